@@ -1,0 +1,174 @@
+/*
+ * mcfgpu.h - C ABI of libmcfgpu.so, the B200 (sm_100a) network-simplex engine.
+ *
+ * The reference (pdegenhardt/MinCostFlow, C#) has no native boundary at all (no DllImport anywhere); this
+ * header DEFINES the boundary at the narrowest seam the reference has: the public solver surface
+ *   IMinCostFlowSolver            src/MinCostFlow.Core/IMinCostFlowSolver.cs:8-34
+ *   NetworkSimplex (the extras)   src/MinCostFlow.Core/Lemon/Algorithms/NetworkSimplex.cs:119-210, :416-587
+ * and follows the pinned-raw-pointer precedent of its private OptimizedPivotWrapper (NetworkSimplex.cs:1699-1722).
+ * Every entry point below names the reference member it replaces.  INTEGRATION.md shows the P/Invoke
+ * declarations a maintainer adds on the C# side (`CudaNetworkSimplex : IMinCostFlowSolver`).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all structs are blittable (sequential layout, no pointers inside).
+ *   - every function returns 0 (MCF_OK) or a negative mcf_error; no exception crosses the ABI.
+ *     The C# / C++ / Python wrappers map codes back to the reference's exceptions:
+ *       MCF_ERR_INVALID_ARGUMENT -> ArgumentException          (NetworkSimplex.cs:155-158, :171-174, :185-188)
+ *       MCF_ERR_NOT_OPTIMAL      -> InvalidOperationException("Solution not optimal")  (NetworkSimplex.cs:418-421)
+ *   - inputs are caller-owned and copied during the call; the handle owns all device and host staging memory;
+ *     results are copied device->host once per solve and served from host memory afterwards
+ *     (SolutionValidator calls GetFlow/GetPotential per element, SolutionValidator.cs:59-78).
+ *   - a handle is not thread-safe (neither is the reference solver); different handles may be used from
+ *     different threads.  There is NO CPU fallback: without an sm_100 device mcf_create fails with
+ *     MCF_ERR_NO_DEVICE.
+ *   - arithmetic: arc ids/endpoints int32; costs must fit int32 on the device (|cost| <= 2^31-1, else
+ *     MCF_ERR_RANGE); flows, capacities, supplies, potentials and reduced costs are int64 as in the
+ *     reference (`long`, NetworkSimplex.cs:42-48).  "Infinite" capacity is INT64_MAX/2 (NetworkSimplex.cs:127).
+ */
+#ifndef MCFGPU_H
+#define MCFGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCF_API_VERSION 1
+#define MCF_INF (INT64_MAX / 2)               /* NetworkSimplex.cs:127 */
+
+typedef enum mcf_error {
+    MCF_OK = 0,
+    MCF_ERR_INVALID_ARGUMENT = -1,            /* bad handle / null pointer / arc or node id out of range */
+    MCF_ERR_NO_DEVICE = -2,                   /* no CUDA device of compute capability 10.x */
+    MCF_ERR_CUDA = -3,                        /* a CUDA runtime call failed; see mcf_last_error */
+    MCF_ERR_OUT_OF_MEMORY = -4,
+    MCF_ERR_NOT_OPTIMAL = -5,                 /* result getter called while Status != Optimal */
+    MCF_ERR_RANGE = -6,                       /* |cost| does not fit int32, or too many arcs (m + 2n >= 2^30) */
+    MCF_ERR_ENGINE_LIMIT = -7,                /* pivot cycle / stem longer than the in-kernel staging buffers */
+    MCF_ERR_TIMEOUT = -8,                     /* a grid barrier timed out (kernel abandoned) */
+    MCF_ERR_NOT_SOLVED = -9                   /* metrics / results requested before mcf_solve */
+} mcf_error;
+
+/* Enum values are the reference's: SolverStatus.cs:7-34, PivotRule.cs:7-40, SupplyType.cs:7-17,
+ * OptimizationFlags in OptimizationTypes.cs:8-20. */
+typedef enum mcf_status { MCF_NOT_SOLVED = 0, MCF_OPTIMAL = 1, MCF_INFEASIBLE = 2, MCF_UNBOUNDED = 3, MCF_UNBALANCED = 4 } mcf_status;
+typedef enum mcf_pivot_rule { MCF_FIRST_ELIGIBLE = 0, MCF_BEST_ELIGIBLE = 1, MCF_BLOCK_SEARCH = 2 } mcf_pivot_rule;
+typedef enum mcf_supply_type { MCF_GEQ = 0, MCF_LEQ = 1 } mcf_supply_type;
+enum {
+    MCF_FLAG_ADAPTIVE_BLOCK_SIZE = 1, MCF_FLAG_SMALL_BLOCKS_FOR_DENSE = 2, MCF_FLAG_REDUCED_COST_CACHING = 4,
+    MCF_FLAG_CANDIDATE_LIST_PIVOT = 8, MCF_FLAG_HOT_COLD_SPLITTING = 16, MCF_FLAG_EARLY_TERMINATION = 32
+};
+
+/* OptimizationConfig (OptimizationTypes.cs:25-38), same defaults via mcf_default_options. */
+typedef struct mcf_optimization_config {
+    int32_t flags;
+    int32_t max_block_size;
+    int32_t min_block_size;
+    int32_t dense_network_threshold;
+    int32_t consecutive_hits_before_adapt;
+    int32_t reserved0;
+    double candidate_list_ratio;
+    double block_size_growth_factor;
+    double block_size_shrink_factor;
+    double low_hit_rate_threshold;
+    double high_hit_rate_threshold;
+    double min_block_size_ratio;
+} mcf_optimization_config;
+
+typedef struct mcf_options {
+    int32_t supply_type;            /* SetSupplyType, NetworkSimplex.cs:197; default MCF_GEQ (:38) */
+    int32_t pivot_rule;             /* SetPivotRule, NetworkSimplex.cs:206; default MCF_BLOCK_SEARCH (:77) */
+    int32_t auto_configuration;     /* SetAutoConfiguration, NetworkSimplex.cs:567; default 1 (:90) */
+    int32_t optimized_pivot;        /* EnableOptimizedPivot, NetworkSimplex.cs:532.  First/Best Eligible: same pivots as
+                                       the managed rules.  Block Search: not supported yet -> MCF_ERR_INVALID_ARGUMENT */
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t max_ctas;               /* 0 = one CTA per SM (cooperative-launch limit) */
+    int32_t lookahead_blocks;       /* blocks priced in the first pricing round of a search; 0 = default (2) */
+    int32_t reserved0;
+    int64_t stop_after_pivots;      /* >0: stop after this many pivots with Status = NotSolved (bounded samples) */
+    double barrier_timeout_s;       /* 0 = default 10 s */
+    mcf_optimization_config config; /* SetOptimizationConfig, NetworkSimplex.cs:557-561 (used when auto_configuration == 0) */
+} mcf_options;
+
+/* SolverMetrics (OptimizationTypes.cs:43-69) + engine counters. */
+typedef struct mcf_metrics {
+    int64_t iterations;                 /* Iterations */
+    int64_t total_arcs_checked;         /* TotalArcsChecked (Block Search rules only, like the reference) */
+    int32_t initial_block_size;         /* InitialBlockSize */
+    int32_t final_block_size;           /* FinalBlockSize */
+    int32_t baseline_iterations;        /* BaselineIterations = (int)(sqrt(S) * n * 0.5), NetworkSimplex.cs:276 */
+    int32_t pricing_kind;               /* 0 First, 1 Best, 2 Block, 3 cached Block (NetworkSimplex.cs:879-885) */
+    double average_arcs_checked_per_pivot;
+    double iteration_ratio;
+    double pivot_search_time_us;        /* PivotSearchTimeMicros  (device time in phase A) */
+    double tree_update_time_us;         /* TreeUpdateTimeMicros + PotentialUpdateTimeMicros: phase C is fused */
+    double cycle_time_us;               /* join + leaving-arc search (phase B); the reference leaves this untimed */
+    double total_solve_time_us;         /* TotalSolveTimeMicros: host wall time of mcf_solve */
+    double kernel_time_us;              /* device time of the persistent kernel (CUDA events) */
+    double h2d_time_us, d2h_time_us, host_prepass_time_us;
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t arcs_priced;                /* arcs whose reduced cost was evaluated on the device */
+    int64_t pricing_bytes;              /* 16 B * arcs_priced (int32 source, target, cost, state) */
+    int64_t degenerate_pivots, cycle_nodes, moved_nodes, max_cycle, max_stem, pricing_rounds;
+    int32_t config_flags;               /* OptimizationFlags actually used (after auto-configuration) */
+    int32_t grid_ctas;
+    double degree_cv;                   /* ProblemCharacteristics.DegreeCV when auto-configured, else 0 */
+} mcf_metrics;
+
+typedef struct mcf_handle mcf_handle;
+
+int mcf_api_version(void);
+/* number of usable sm_100 devices (0 when none) */
+int mcf_device_count(void);
+void mcf_default_options(mcf_options* out);
+
+/* new NetworkSimplex(graph): NetworkSimplex.cs:119-148 + InitializeGraphStructure :605-622.
+ * source/target: arc endpoints in arc-id order (CompactDigraph.cs:110-126). */
+int mcf_create(int32_t n, int32_t m, const int32_t* source, const int32_t* target, mcf_handle** out);
+void mcf_destroy(mcf_handle* h);
+
+/* SetArcBounds / SetArcCost for all arcs at once (NetworkSimplex.cs:153-178).  NULL keeps the defaults
+ * lower = 0, upper = MCF_INF, cost = 0 (NetworkSimplex.cs:615-617). */
+int mcf_set_arcs(mcf_handle* h, const int64_t* lower, const int64_t* upper, const int64_t* cost);
+/* SetNodeSupply for all nodes (NetworkSimplex.cs:183-192). */
+int mcf_set_supply(mcf_handle* h, const int64_t* supply);
+/* SetSupplyType / SetPivotRule / EnableOptimizedPivot / SetOptimizationConfig / SetAutoConfiguration. */
+int mcf_set_options(mcf_handle* h, const mcf_options* opt);
+
+/* Solve(): NetworkSimplex.cs:215-411.  *status_out receives a mcf_status. */
+int mcf_solve(mcf_handle* h, int32_t* status_out);
+int mcf_get_status(mcf_handle* h, int32_t* status_out);           /* Status, NetworkSimplex.cs:470 */
+
+/* GetFlow / GetPotential / GetTotalCost (NetworkSimplex.cs:416-465): MCF_ERR_NOT_OPTIMAL unless Optimal. */
+int mcf_get_flows(mcf_handle* h, int64_t* out_m);
+int mcf_get_potentials(mcf_handle* h, int64_t* out_n);
+int mcf_get_flow(mcf_handle* h, int32_t arc, int64_t* out);
+int mcf_get_potential(mcf_handle* h, int32_t node, int64_t* out);
+int mcf_get_total_cost(mcf_handle* h, int64_t* out);
+/* GetNodeSupply / GetArcCost / GetArcLowerBound / GetArcUpperBound (NetworkSimplex.cs:480-527), including the
+ * reference's post-solve quirk that the upper bound is returned shifted by the lower bound (:647-651). */
+int mcf_get_node_supply(mcf_handle* h, int32_t node, int64_t* out);
+int mcf_get_arc_cost(mcf_handle* h, int32_t arc, int64_t* out);
+int mcf_get_arc_lower_bound(mcf_handle* h, int32_t arc, int64_t* out);
+int mcf_get_arc_upper_bound(mcf_handle* h, int32_t arc, int64_t* out);
+
+int mcf_get_metrics(mcf_handle* h, mcf_metrics* out);             /* GetMetrics, NetworkSimplex.cs:584 */
+
+/* Batches of independent instances (BASELINE.json config 5): instance i is solved on devices[i % n_devices],
+ * one host thread per device.  statuses_out[count] receives each instance's mcf_status. */
+int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out);
+
+/* Roofline probe: uploads the handle's initial basis and runs the stand-alone Best Eligible pricing sweep
+ * (one full pass over all S = m + n arcs, 16 B of arc data per arc) `reps` times, timing each launch with CUDA
+ * events on the handle's stream.  ms_out[reps] receives the per-launch times, *entering_arc_out the arg-min arc
+ * (lowest id among ties, -1 if none).  When flush_l2 != 0 a buffer larger than L2 is overwritten between launches. */
+int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_out, int32_t* entering_arc_out,
+                      int64_t* arcs_per_launch_out);
+
+const char* mcf_last_error(mcf_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCFGPU_H */

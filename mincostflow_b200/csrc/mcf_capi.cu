@@ -1,0 +1,661 @@
+// mcf_capi.cu - host layer of libmcfgpu.so: the C ABI declared in include/mcfgpu.h.
+//
+// Mirrors the host-side part of NetworkSimplex.Solve() (NS.cs = src/MinCostFlow.Core/Lemon/Algorithms/
+// NetworkSimplex.cs in the reference): CheckBounds (:624), TransformToStandardForm (:636), the automatic
+// configuration (ProblemAnalyzer.cs:21-62 -> OptimizationSelector.cs:14-96), Initialize (:671-845), the choice of
+// pricing rule (:847-886), and after the pivot loop the status / result plumbing (:359-410).  The pivot loop itself
+// runs in mcf_kernels.cu.  There is no CPU solver in this library.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mcfgpu.h"
+#include "mcf_device.cuh"
+
+extern "C" int mcfk_pivot_smem_bytes();
+extern "C" int mcfk_max_grid(int device, int* sm_count);
+extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream);
+extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+inline double us_since(clk::time_point t0) { return std::chrono::duration<double, std::micro>(clk::now() - t0).count(); }
+
+constexpr int64_t kInf = std::numeric_limits<int64_t>::max() / 2;   // NS.cs:127
+
+struct Characteristics {            // the subset of ProblemCharacteristics the selector reads
+    int node_count = 0, arc_count = 0;
+    double density = 0, degree_cv = 0, cost_cv = 0;
+    bool is_dense = false, is_sparse = false, has_uniform_costs = false;
+    int source_count = 0, sink_count = 0, transshipment_count = 0;
+    int64_t max_abs_supply = 0;
+    int detected_type = 0;          // 0 General, 1 Circulation, 2 Assignment, 3 Transportation, 4 Transshipment
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct mcf_handle {
+    int n = 0, m = 0;
+    std::vector<int32_t> source, target;
+    std::vector<int64_t> lower, upper, cost, supply, orig_lower;      // NS.cs:42-48 (mutated by Solve like the reference)
+    mcf_options opt{};
+    int status = MCF_NOT_SOLVED;
+    bool solved_once = false;
+    std::vector<int64_t> flow, pi;                                    // results, host side
+    int64_t total_cost = 0;
+    mcf_metrics metrics{};
+    std::string err;
+    // device
+    int device_bound = -1;
+    cudaStream_t stream = nullptr;
+    DevBuf<int> d_src, d_tgt, d_cost, d_state, d_in, d_sz, d_parent, d_pd;
+    DevBuf<long long> d_flow, d_upper, d_lower, d_pi, d_rc;
+    DevBuf<mcf::PriceRec> d_part;
+    DevBuf<mcf::CycEnt> d_list;
+    DevBuf<mcf::Ctl> d_ctl;
+    DevBuf<unsigned char> d_flush;
+    // host staging for the initial basis
+    std::vector<int> h_src, h_tgt, h_cost, h_state, h_in, h_sz, h_parent, h_pd;
+    std::vector<long long> h_flow, h_upper, h_pi;
+};
+
+namespace {
+
+int fail(mcf_handle* h, int code, const char* fmt, ...)
+{
+    if (h) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fail((h), e__ == cudaErrorMemoryAllocation ? MCF_ERR_OUT_OF_MEMORY : MCF_ERR_CUDA,       \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                                   \
+    } while (0)
+
+bool device_ok(int dev)
+{
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return false;
+    return p.major == 10;           // sm_100a code only
+}
+
+// ProblemAnalyzer.Analyze (ProblemAnalyzer.cs:21-62); only what OptimizationSelector consumes.
+Characteristics analyze(const mcf_handle& h)
+{
+    Characteristics ch;
+    const int n = h.n, m = h.m;
+    ch.node_count = n; ch.arc_count = m;
+    const int64_t max_possible = (int64_t)n * (n - 1);
+    ch.density = max_possible > 0 ? (double)m / (double)max_possible : 0;
+    std::vector<int> outd(n > 0 ? n : 1, 0), ind(n > 0 ? n : 1, 0);
+    for (int e = 0; e < m; ++e) { outd[h.source[e]]++; ind[h.target[e]]++; }
+    int total = 0;
+    for (int i = 0; i < n; ++i) total += outd[i] + ind[i];
+    const double avg = n > 0 ? (double)total / n : 0;
+    double var = 0;
+    if (n > 0) { for (int i = 0; i < n; ++i) { const double d = (outd[i] + ind[i]) - avg; var += d * d; } var /= n; }   // :86-95
+    ch.degree_cv = avg > 0 ? std::sqrt(var) / avg : 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t s = h.supply[i];
+        if (s > 0) ch.source_count++; else if (s < 0) ch.sink_count++; else ch.transshipment_count++;
+        const int64_t a = s < 0 ? -s : s; if (a > ch.max_abs_supply) ch.max_abs_supply = a;
+    }
+    if (m == 0) ch.has_uniform_costs = true;
+    else {
+        int64_t tot = 0;
+        for (int i = 0; i < m; ++i) tot += h.cost[i];
+        const double ac = (double)tot / m;
+        double v = 0;
+        for (int i = 0; i < m; ++i) { const double d = h.cost[i] - ac; v += d * d; }
+        v /= m;
+        ch.cost_cv = std::fabs(ac) > 0 ? std::sqrt(v) / std::fabs(ac) : 0;
+        ch.has_uniform_costs = ch.cost_cv < 0.01;
+    }
+    if (ch.source_count == 0 && ch.sink_count == 0) ch.detected_type = 1;
+    else {
+        int only_out = 0, only_in = 0;
+        for (int i = 0; i < n; ++i) {
+            if (outd[i] > 0 && ind[i] == 0) only_out++; else if (outd[i] == 0 && ind[i] > 0) only_in++;
+        }
+        const bool bip = ((double)(only_out + only_in) / n) > 0.8;
+        if (bip && ch.max_abs_supply == 1 && ch.source_count == ch.sink_count) ch.detected_type = 2;
+        else if (bip && ch.transshipment_count == 0) ch.detected_type = 3;
+        else if (ch.transshipment_count > 0) ch.detected_type = 4;
+    }
+    ch.is_dense = ch.density > 0.01 || m > 10000;
+    ch.is_sparse = ch.density < 0.005;
+    return ch;
+}
+
+void default_config(mcf_optimization_config* c)
+{   // OptimizationTypes.cs:25-38
+    c->flags = 0; c->max_block_size = 100; c->min_block_size = 25; c->dense_network_threshold = 10000;
+    c->consecutive_hits_before_adapt = 3; c->reserved0 = 0; c->candidate_list_ratio = 0.1;
+    c->block_size_growth_factor = 1.2; c->block_size_shrink_factor = 0.8; c->low_hit_rate_threshold = 0.05;
+    c->high_hit_rate_threshold = 0.3; c->min_block_size_ratio = 0.125;
+}
+
+// OptimizationSelector.SelectConfiguration (OptimizationSelector.cs:14-96)
+mcf_optimization_config select_config(const Characteristics& ch)
+{
+    mcf_optimization_config c; default_config(&c);
+    int flags = 0;
+    if (ch.is_dense) { flags |= MCF_FLAG_SMALL_BLOCKS_FOR_DENSE; c.min_block_size = 10; c.max_block_size = 50; c.dense_network_threshold = 5000; }
+    if (ch.degree_cv > 0.5) {
+        flags |= MCF_FLAG_ADAPTIVE_BLOCK_SIZE;
+        c.block_size_growth_factor = 1.3; c.block_size_shrink_factor = 0.7; c.consecutive_hits_before_adapt = 2;
+    } else if (ch.degree_cv > 0.3) flags |= MCF_FLAG_ADAPTIVE_BLOCK_SIZE;
+    if (ch.is_sparse && ch.arc_count < 50000) flags |= MCF_FLAG_REDUCED_COST_CACHING;
+    const bool transp = ch.detected_type == 2 || ch.detected_type == 3;
+    if (ch.arc_count >= 1000 && ((ch.is_sparse && ch.arc_count > 5000) || ch.has_uniform_costs || transp)) {
+        flags |= MCF_FLAG_CANDIDATE_LIST_PIVOT;         // set but never read by the solver (inert)
+        c.candidate_list_ratio = ch.has_uniform_costs ? 0.2 : (ch.arc_count > 100000 ? 0.05 : 0.1);
+    }
+    if (ch.node_count > 5000 && ch.degree_cv > 1.0) flags |= MCF_FLAG_HOT_COLD_SPLITTING;
+    if (transp) flags |= MCF_FLAG_EARLY_TERMINATION;
+    c.low_hit_rate_threshold = ch.arc_count > 10000 ? 0.03 : 0.05;
+    c.high_hit_rate_threshold = ch.arc_count > 10000 ? 0.25 : 0.3;
+    c.min_block_size_ratio = ch.arc_count > 100000 ? 0.0625 : (ch.arc_count > 10000 ? 0.125 : 0.25);
+    c.flags = flags;
+    return c;
+}
+
+int bind_device(mcf_handle* h)
+{
+    const int dev = h->opt.device;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fail(h, MCF_ERR_NO_DEVICE, "no CUDA device visible");
+    if (dev < 0 || dev >= count || !device_ok(dev)) return fail(h, MCF_ERR_NO_DEVICE, "device %d is not an sm_100 GPU", dev);
+    CUDA_TRY(h, cudaSetDevice(dev));
+    if (h->device_bound != dev) {
+        if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
+        h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
+        h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
+        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->device_bound = dev;
+    }
+    return MCF_OK;
+}
+
+// Initialize() + InitializeGEQ / InitializeLEQ (NS.cs:671-845) into the staging arrays, in the engine's layout:
+// the star tree rooted at node n, labelled in[u] = u + 1 (the reference's initial thread order root,0,1,..,n-1).
+void build_initial_basis(mcf_handle* h, int64_t art_cost)
+{
+    const int n = h->n, m = h->m, S = m + n, A = m + 2 * n, root = n;
+    h->h_src.assign(S, 0); h->h_tgt.assign(S, 0); h->h_cost.assign(S, 0);
+    h->h_state.assign(A, mcf::STATE_LOWER); h->h_flow.assign(A, 0); h->h_upper.assign(A, kInf);
+    h->h_in.resize(n + 1); h->h_sz.resize(n + 1); h->h_parent.resize(n + 1); h->h_pd.resize(n + 1); h->h_pi.assign(n + 1, 0);
+    for (int e = 0; e < m; ++e) {
+        h->h_src[e] = h->source[e]; h->h_tgt[e] = h->target[e]; h->h_cost[e] = (int)h->cost[e];
+        h->h_upper[e] = h->upper[e];
+    }
+    const bool geq = h->opt.supply_type == MCF_GEQ;
+    int f = S;
+    for (int u = 0, e = m; u < n; ++u, ++e) {
+        h->h_in[u] = u + 1; h->h_sz[u] = 1; h->h_parent[u] = root;
+        const int64_t s = h->supply[u];
+        if (geq) { h->h_src[e] = root; h->h_tgt[e] = u; } else { h->h_src[e] = u; h->h_tgt[e] = root; }
+        const bool plain = geq ? s <= 0 : s >= 0;
+        if (plain) {                                        // NS.cs:744-754 / :811-821
+            h->h_pd[u] = e * 2 + (geq ? 0 : 1);
+            h->h_pi[u] = 0; h->h_flow[e] = geq ? -s : s; h->h_state[e] = mcf::STATE_TREE;
+        } else {                                            // NS.cs:755-771 / :822-838: artificial arc f carries the supply
+            h->h_pd[u] = f * 2 + (geq ? 1 : 0);
+            h->h_pi[u] = geq ? -art_cost : art_cost;
+            h->h_flow[f] = geq ? s : -s; h->h_state[f] = mcf::STATE_TREE;
+            h->h_state[e] = mcf::STATE_LOWER; h->h_flow[e] = 0;
+            ++f;
+        }
+    }
+    h->h_in[root] = 0; h->h_sz[root] = n + 1; h->h_parent[root] = -1; h->h_pd[root] = -2;
+}
+
+int upload_basis(mcf_handle* h, bool need_cache, int grid)
+{
+    const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
+    CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
+    CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
+    CUDA_TRY(h, h->d_in.ensure(n + 1)); CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_parent.ensure(n + 1));
+    CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_pi.ensure(n + 1));
+    CUDA_TRY(h, h->d_part.ensure((size_t)2 * grid)); CUDA_TRY(h, h->d_list.ensure((size_t)n + 1)); CUDA_TRY(h, h->d_ctl.ensure(1));
+    if (need_cache) { CUDA_TRY(h, h->d_rc.ensure(S)); CUDA_TRY(h, cudaMemsetAsync(h->d_rc.p, 0, (size_t)S * 8, h->stream)); }
+    cudaStream_t st = h->stream;
+    int64_t bytes = 0;
+    auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };
+    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)S * 4));
+    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
+    CUDA_TRY(h, up(h->d_flow.p, h->h_flow.data(), (size_t)A * 8)); CUDA_TRY(h, up(h->d_upper.p, h->h_upper.data(), (size_t)A * 8));
+    CUDA_TRY(h, up(h->d_in.p, h->h_in.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4));
+    CUDA_TRY(h, up(h->d_parent.p, h->h_parent.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4));
+    CUDA_TRY(h, up(h->d_pi.p, h->h_pi.data(), (size_t)(n + 1) * 8));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(mcf::Ctl), st));
+    h->metrics.h2d_bytes = bytes;
+    return MCF_OK;
+}
+
+void fill_params(mcf_handle* h, mcf::Params* P)
+{
+    std::memset(P, 0, sizeof(*P));
+    P->n = h->n; P->m = h->m; P->S = h->m + h->n; P->A = h->m + 2 * h->n;
+    P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p;
+    P->flow = h->d_flow.p; P->upper = h->d_upper.p; P->orig_lower = nullptr; P->rc_cache = nullptr;
+    P->in = h->d_in.p; P->sz = h->d_sz.p; P->parent = h->d_parent.p; P->pd = h->d_pd.p; P->pi = h->d_pi.p;
+    P->part = h->d_part.p; P->list = h->d_list.p; P->list_cap = h->n + 1; P->ctl = h->d_ctl.p;
+}
+
+int choose_grid(mcf_handle* h, int* sms_out)
+{
+    int sms = 0;
+    const int maxg = mcfk_max_grid(h->opt.device, &sms);
+    if (maxg <= 0) return fail(h, MCF_ERR_CUDA, "cooperative occupancy query failed (%d): %s", maxg, cudaGetErrorString(cudaGetLastError()));
+    int g = maxg;
+    if (h->opt.max_ctas > 0 && h->opt.max_ctas < g) g = h->opt.max_ctas;
+    else if (h->opt.max_ctas <= 0) {
+        // small instances: fewer CTAs make every grid barrier cheaper; keep >= 2048 nodes or 16K arcs per CTA
+        const int64_t S = (int64_t)h->m + h->n;
+        int64_t want = std::max<int64_t>((h->n + 2047) / 2048, (S + 16383) / 16384);
+        if (want < 4) want = 4;
+        if (want < g) g = (int)want;
+    }
+    if (sms_out) *sms_out = sms;
+    return g;
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+
+extern "C" {
+
+int mcf_api_version(void) { return MCF_API_VERSION; }
+
+int mcf_device_count(void)
+{
+    int count = 0, ok = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int d = 0; d < count; ++d) ok += device_ok(d) ? 1 : 0;
+    return ok;
+}
+
+void mcf_default_options(mcf_options* o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->supply_type = MCF_GEQ; o->pivot_rule = MCF_BLOCK_SEARCH; o->auto_configuration = 1; o->optimized_pivot = 0;
+    o->device = 0; o->max_ctas = 0; o->lookahead_blocks = 0; o->stop_after_pivots = 0; o->barrier_timeout_s = 0;
+    default_config(&o->config);
+}
+
+int mcf_create(int32_t n, int32_t m, const int32_t* source, const int32_t* target, mcf_handle** out)
+{
+    if (!out) return MCF_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (n < 0 || m < 0 || (m > 0 && (!source || !target))) return MCF_ERR_INVALID_ARGUMENT;
+    if ((int64_t)m + 2 * (int64_t)n >= (1LL << 30)) return MCF_ERR_RANGE;
+    for (int e = 0; e < m; ++e)
+        if (source[e] < 0 || source[e] >= n || target[e] < 0 || target[e] >= n) return MCF_ERR_INVALID_ARGUMENT;
+    if (mcf_device_count() <= 0) return MCF_ERR_NO_DEVICE;          // no CPU fallback
+    mcf_handle* h = new (std::nothrow) mcf_handle();
+    if (!h) return MCF_ERR_OUT_OF_MEMORY;
+    h->n = n; h->m = m;
+    h->source.assign(source, source + m); h->target.assign(target, target + m);
+    h->lower.assign(m, 0); h->upper.assign(m, kInf); h->cost.assign(m, 0); h->orig_lower.assign(m, 0);   // NS.cs:615-617
+    h->supply.assign(n, 0);
+    mcf_default_options(&h->opt);
+    *out = h;
+    return MCF_OK;
+}
+
+void mcf_destroy(mcf_handle* h)
+{
+    if (!h) return;
+    if (h->device_bound >= 0) {
+        cudaSetDevice(h->device_bound);
+        h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
+        h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
+        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+int mcf_set_arcs(mcf_handle* h, const int64_t* lower, const int64_t* upper, const int64_t* cost)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    const int m = h->m;
+    if (lower) { h->lower.assign(lower, lower + m); h->orig_lower.assign(lower, lower + m); }       // NS.cs:160-162
+    if (upper) h->upper.assign(upper, upper + m);
+    if (cost) h->cost.assign(cost, cost + m);
+    return MCF_OK;
+}
+
+int mcf_set_supply(mcf_handle* h, const int64_t* supply)
+{
+    if (!h || (!supply && h->n > 0)) return MCF_ERR_INVALID_ARGUMENT;
+    h->supply.assign(supply, supply + h->n);
+    return MCF_OK;
+}
+
+int mcf_set_options(mcf_handle* h, const mcf_options* opt)
+{
+    if (!h || !opt) return MCF_ERR_INVALID_ARGUMENT;
+    if (opt->supply_type != MCF_GEQ && opt->supply_type != MCF_LEQ) return fail(h, MCF_ERR_INVALID_ARGUMENT, "unknown supply type %d", opt->supply_type);
+    if (opt->pivot_rule < MCF_FIRST_ELIGIBLE || opt->pivot_rule > MCF_BLOCK_SEARCH)
+        return fail(h, MCF_ERR_INVALID_ARGUMENT, "pivot rule %d not implemented yet", opt->pivot_rule);   // NS.cs:884
+    if (opt->optimized_pivot && opt->pivot_rule == MCF_BLOCK_SEARCH)
+        return fail(h, MCF_ERR_INVALID_ARGUMENT, "optimized Block Search pivot (BlockSearchPivotOptimized.cs) is not supported by the CUDA engine yet");
+    h->opt = *opt;
+    return MCF_OK;
+}
+
+int mcf_solve(mcf_handle* h, int32_t* status_out)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    const auto t_total = clk::now();
+    h->metrics = mcf_metrics{};
+    h->status = MCF_NOT_SOLVED;
+    const int n = h->n, m = h->m, S = m + n;
+    auto done = [&](int st) { h->status = st; h->solved_once = true; if (status_out) *status_out = st; h->metrics.total_solve_time_us = us_since(t_total); return MCF_OK; };
+
+    int rc = bind_device(h);
+    if (rc != MCF_OK) return rc;
+
+    const auto t_pre = clk::now();
+    for (int i = 0; i < m; ++i) if (h->upper[i] < h->lower[i]) return done(MCF_INFEASIBLE);          // CheckBounds, NS.cs:624-634
+    bool has_lower = false;
+    for (int i = 0; i < m; ++i) {                                                                     // NS.cs:639-653
+        if (h->lower[i] != 0) {
+            h->supply[h->source[i]] -= h->lower[i]; h->supply[h->target[i]] += h->lower[i];
+            h->upper[i] -= h->lower[i]; h->lower[i] = 0;
+        }
+        has_lower |= h->orig_lower[i] != 0;
+    }
+    int64_t max_cost = 0;
+    for (int i = 0; i < m; ++i) { const int64_t a = h->cost[i] < 0 ? -h->cost[i] : h->cost[i]; if (a > max_cost) max_cost = a; }
+    if (max_cost > std::numeric_limits<int32_t>::max()) return fail(h, MCF_ERR_RANGE, "|cost| = %lld does not fit the device's int32 cost array", (long long)max_cost);
+    const int64_t art_cost = (max_cost + 1) * n;                                                      // NS.cs:663-668
+
+    mcf_optimization_config cfg = h->opt.config;
+    if (h->opt.auto_configuration) {                                                                  // NS.cs:237-250
+        const Characteristics ch = analyze(*h);
+        cfg = select_config(ch);
+        h->metrics.degree_cv = ch.degree_cv;
+    }
+    h->metrics.config_flags = cfg.flags;
+
+    // CreatePivotRuleFinder, NS.cs:847-886 (+ BlockSearchPivot ctor :1304-1337)
+    int kind = h->opt.pivot_rule;
+    if (!h->opt.optimized_pivot && h->opt.pivot_rule == MCF_BLOCK_SEARCH && (cfg.flags & MCF_FLAG_REDUCED_COST_CACHING)) kind = mcf::PK_BLOCK_CACHED;
+    int block = 0, dyn_min = 0;
+    if (kind == mcf::PK_BLOCK || kind == mcf::PK_BLOCK_CACHED) {
+        const int base = (int)std::sqrt((double)S);
+        const int r = (int)(base * cfg.min_block_size_ratio);
+        dyn_min = cfg.min_block_size > r ? cfg.min_block_size : r;
+        if (cfg.flags & MCF_FLAG_SMALL_BLOCKS_FOR_DENSE) {
+            const double density = (double)S / n;
+            block = density > 10 ? std::min(50, base / 4) : base;
+        } else block = base;
+        block = std::max(block, dyn_min);
+        h->metrics.initial_block_size = block;
+    }
+    h->metrics.pricing_kind = kind;
+    h->metrics.baseline_iterations = (int)(std::sqrt((double)S) * n * 0.5);                           // NS.cs:276
+
+    if (n == 0) { h->flow.assign(m, 0); h->pi.clear(); h->total_cost = 0; return done(MCF_OPTIMAL); }
+
+    build_initial_basis(h, art_cost);
+    h->metrics.host_prepass_time_us = us_since(t_pre);
+
+    int sms = 0;
+    const int grid = choose_grid(h, &sms);
+    if (grid <= 0) return grid;
+    h->metrics.grid_ctas = grid;
+
+    const auto t_h2d = clk::now();
+    rc = upload_basis(h, kind == mcf::PK_BLOCK_CACHED, grid);
+    if (rc != MCF_OK) return rc;
+    mcf::Params P; fill_params(h, &P);
+    if (has_lower) {
+        CUDA_TRY(h, h->d_lower.ensure(m));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_lower.p, h->orig_lower.data(), (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+        h->metrics.h2d_bytes += (int64_t)m * 8;
+        P.orig_lower = h->d_lower.p;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->metrics.h2d_time_us = us_since(t_h2d);
+
+    P.rc_cache = kind == mcf::PK_BLOCK_CACHED ? h->d_rc.p : nullptr;
+    P.kind = kind; P.block_size = block > 0 ? block : 1; P.dyn_min_block = dyn_min; P.max_block_size = cfg.max_block_size;
+    P.adaptive = (cfg.flags & MCF_FLAG_ADAPTIVE_BLOCK_SIZE) ? 1 : 0; P.consecutive = cfg.consecutive_hits_before_adapt;
+    P.low_thr = cfg.low_hit_rate_threshold; P.high_thr = cfg.high_hit_rate_threshold;
+    P.shrink = cfg.block_size_shrink_factor; P.grow = cfg.block_size_growth_factor;
+    P.lookahead0 = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : 2;
+    P.max_iterations = std::max<int64_t>(1000000LL, (int64_t)n * m);                                  // NS.cs:280
+    P.stop_after = h->opt.stop_after_pivots;
+    const double tmo = h->opt.barrier_timeout_s > 0 ? h->opt.barrier_timeout_s : 10.0;
+    P.barrier_timeout_cycles = (unsigned long long)(tmo * 1.9e9);
+
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(h, cudaEventCreate(&ev0)); CUDA_TRY(h, cudaEventCreate(&ev1));
+    CUDA_TRY(h, cudaEventRecord(ev0, h->stream));
+    const int lrc = mcfk_launch_pivot(&P, grid, h->stream);
+    if (lrc != 0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(h, MCF_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); }
+    CUDA_TRY(h, cudaEventRecord(ev1, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(h, MCF_ERR_CUDA, "pivot kernel failed: %s", cudaGetErrorString(se)); }
+    float kms = 0; cudaEventElapsedTime(&kms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    h->metrics.kernel_time_us = kms * 1000.0;
+
+    const auto t_d2h = clk::now();
+    mcf::Ctl ctl;
+    CUDA_TRY(h, cudaMemcpyAsync(&ctl, h->d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+    h->flow.resize(m); h->pi.resize(n);
+    CUDA_TRY(h, cudaMemcpyAsync(h->flow.data(), h->d_flow.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->pi.data(), h->d_pi.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->metrics.d2h_time_us = us_since(t_d2h);
+    h->metrics.d2h_bytes = (int64_t)m * 8 + (int64_t)n * 8 + (int64_t)sizeof(ctl);
+
+    mcf_metrics& M = h->metrics;
+    M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = (kind >= 2) ? ctl.final_block_size : 0;
+    M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
+    M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
+    M.pivot_search_time_us = ctl.ns_price / 1000.0; M.cycle_time_us = ctl.ns_cycle / 1000.0; M.tree_update_time_us = ctl.ns_update / 1000.0;
+    M.degenerate_pivots = ctl.degenerate; M.cycle_nodes = ctl.cycle_nodes; M.moved_nodes = ctl.moved_nodes;
+    M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
+    if (kind == mcf::PK_BEST) M.arcs_priced = ctl.pricing_rounds * (int64_t)S;
+    else if (kind == mcf::PK_FIRST) M.arcs_priced = 0;       // not tracked for First Eligible
+    else M.arcs_priced = ctl.arcs_checked;
+    M.pricing_bytes = 16 * M.arcs_priced;
+    h->total_cost = ctl.total_cost;
+
+    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "grid barrier timed out after %lld pivots", (long long)ctl.iterations); }
+    if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
+        done(MCF_NOT_SOLVED);
+        return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: cycle/stem exceeds the in-kernel staging buffer (%d / %d entries)", (long long)ctl.iterations, mcf::kListSmem, mcf::kStemCap);
+    }
+    int st;
+    switch (ctl.status) {
+        case mcf::ST_OPTIMAL: st = ctl.infeasible ? MCF_INFEASIBLE : MCF_OPTIMAL; break;             // NS.cs:360-393
+        case mcf::ST_INFEASIBLE: st = MCF_INFEASIBLE; break;
+        case mcf::ST_UNBOUNDED: st = MCF_UNBOUNDED; break;
+        default: st = MCF_NOT_SOLVED; break;
+    }
+    if (st == MCF_OPTIMAL && has_lower) {                                                            // NS.cs:375-388 (supplies)
+        for (int i = 0; i < m; ++i) if (h->orig_lower[i] != 0) { h->supply[h->source[i]] += h->orig_lower[i]; h->supply[h->target[i]] -= h->orig_lower[i]; }
+    }
+    return done(st);
+}
+
+int mcf_get_status(mcf_handle* h, int32_t* out) { if (!h || !out) return MCF_ERR_INVALID_ARGUMENT; *out = h->status; return MCF_OK; }
+
+int mcf_get_flows(mcf_handle* h, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");
+    std::memcpy(out, h->flow.data(), (size_t)h->m * 8);
+    return MCF_OK;
+}
+int mcf_get_potentials(mcf_handle* h, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");
+    std::memcpy(out, h->pi.data(), (size_t)h->n * 8);
+    return MCF_OK;
+}
+int mcf_get_flow(mcf_handle* h, int32_t arc, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");       // NS.cs:418-421
+    if (arc < 0 || arc >= h->m) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid arc");              // NS.cs:423-426
+    *out = h->flow[arc];
+    return MCF_OK;
+}
+int mcf_get_potential(mcf_handle* h, int32_t node, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");
+    if (node < 0 || node >= h->n) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid node");
+    *out = h->pi[node];
+    return MCF_OK;
+}
+int mcf_get_total_cost(mcf_handle* h, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");
+    *out = h->total_cost;
+    return MCF_OK;
+}
+int mcf_get_node_supply(mcf_handle* h, int32_t node, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (node < 0 || node >= h->n) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid node");
+    *out = h->supply[node]; return MCF_OK;
+}
+int mcf_get_arc_cost(mcf_handle* h, int32_t arc, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (arc < 0 || arc >= h->m) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid arc");
+    *out = h->cost[arc]; return MCF_OK;
+}
+int mcf_get_arc_lower_bound(mcf_handle* h, int32_t arc, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (arc < 0 || arc >= h->m) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid arc");
+    *out = h->orig_lower[arc]; return MCF_OK;                                                         // NS.cs:513
+}
+int mcf_get_arc_upper_bound(mcf_handle* h, int32_t arc, int64_t* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (arc < 0 || arc >= h->m) return fail(h, MCF_ERR_INVALID_ARGUMENT, "Invalid arc");
+    *out = h->upper[arc]; return MCF_OK;                                                              // NS.cs:526 (shifted after Solve)
+}
+
+int mcf_get_metrics(mcf_handle* h, mcf_metrics* out)
+{
+    if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
+    if (!h->solved_once) return fail(h, MCF_ERR_NOT_SOLVED, "Solve() has not been called");
+    *out = h->metrics; return MCF_OK;
+}
+
+int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out)
+{
+    if (!hs || count < 0 || !devices || n_devices <= 0) return MCF_ERR_INVALID_ARGUMENT;
+    std::vector<int> rcs(n_devices, MCF_OK);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_devices; ++d) {
+        workers.emplace_back([&, d]() {
+            for (int i = d; i < count; i += n_devices) {
+                if (!hs[i]) { rcs[d] = MCF_ERR_INVALID_ARGUMENT; continue; }
+                hs[i]->opt.device = devices[d];
+                int32_t st = MCF_NOT_SOLVED;
+                const int rc = mcf_solve(hs[i], &st);
+                if (statuses_out) statuses_out[i] = st;
+                if (rc != MCF_OK && rcs[d] == MCF_OK) rcs[d] = rc;
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int d = 0; d < n_devices; ++d) if (rcs[d] != MCF_OK) return rcs[d];
+    return MCF_OK;
+}
+
+int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_out, int32_t* entering_arc_out, int64_t* arcs_out)
+{
+    if (!h || reps <= 0 || !ms_out) return MCF_ERR_INVALID_ARGUMENT;
+    int rc = bind_device(h);
+    if (rc != MCF_OK) return rc;
+    const int n = h->n, m = h->m, S = m + n;
+    // same pre-pass as mcf_solve, on copies: the probe must not disturb the handle's problem data
+    std::vector<int64_t> sv_supply = h->supply, sv_upper = h->upper;
+    for (int i = 0; i < m; ++i) if (h->lower[i] != 0) { h->supply[h->source[i]] -= h->lower[i]; h->supply[h->target[i]] += h->lower[i]; h->upper[i] -= h->lower[i]; }
+    int64_t max_cost = 0;
+    for (int i = 0; i < m; ++i) { const int64_t a = h->cost[i] < 0 ? -h->cost[i] : h->cost[i]; if (a > max_cost) max_cost = a; }
+    if (max_cost > std::numeric_limits<int32_t>::max()) { h->supply = sv_supply; h->upper = sv_upper; return fail(h, MCF_ERR_RANGE, "cost range"); }
+    build_initial_basis(h, (max_cost + 1) * n);
+    h->supply = sv_supply; h->upper = sv_upper;
+    int sms = 0;
+    const int maxg = mcfk_max_grid(h->opt.device, &sms);
+    if (maxg <= 0) return fail(h, MCF_ERR_CUDA, "occupancy query failed");
+    const int grid = sms;                           // one CTA per SM
+    rc = upload_basis(h, false, grid);
+    if (rc != MCF_OK) return rc;
+    mcf::Params P; fill_params(h, &P);
+    P.kind = mcf::PK_BEST;
+    const size_t flush_bytes = 256u << 20;          // > 126 MB L2
+    if (flush_l2) CUDA_TRY(h, h->d_flush.ensure(flush_bytes));
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(h, cudaEventCreate(&ev0)); CUDA_TRY(h, cudaEventCreate(&ev1));
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) CUDA_TRY(h, cudaMemsetAsync(h->d_flush.p, r & 0xff, flush_bytes, h->stream));
+        CUDA_TRY(h, cudaEventRecord(ev0, h->stream));
+        const int lrc = mcfk_launch_price_sweep(&P, h->d_part.p, grid, h->stream);
+        if (lrc != 0) return fail(h, MCF_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+        CUDA_TRY(h, cudaEventRecord(ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaEventElapsedTime(&ms_out[r], ev0, ev1));
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    std::vector<mcf::PriceRec> recs(grid);
+    CUDA_TRY(h, cudaMemcpy(recs.data(), h->d_part.p, sizeof(mcf::PriceRec) * grid, cudaMemcpyDeviceToHost));
+    long long bc = 0; int ba = -1;
+    for (int g = 0; g < grid; ++g) if (recs[g].c < bc || (recs[g].c == bc && recs[g].c < 0 && recs[g].arc < ba)) { bc = recs[g].c; ba = recs[g].arc; }
+    if (entering_arc_out) *entering_arc_out = ba;
+    if (arcs_out) *arcs_out = S;
+    return MCF_OK;
+}
+
+const char* mcf_last_error(mcf_handle* h) { return h ? h->err.c_str() : "invalid handle"; }
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// mcf_device.cuh - device-side data layout shared by the kernels and the host layer of libmcfgpu.
+//
+// The reference keeps the spanning tree as parent/pred/thread/rev_thread/succ_num/last_succ linked lists
+// (DataStructures/SpanningTree.cs:41-45) and walks them one node at a time.  On a GPU a dependent L2 load
+// costs ~130 ns, so a 100-step walk is already slower than a CPU.  This engine therefore replaces the
+// *unobservable* part of that structure (thread, rev_thread, last_succ, succ_num) by a nested-interval
+// labelling: every node u carries in[u] = its index in a depth-first order of the current basis tree and
+// sz[u] = the size of its subtree, so "v is in the subtree of u" is the O(1) test
+// in[u] <= in[v] < in[u] + sz[u].  With that test every per-pivot step of NetworkSimplex.cs:925-1209 becomes a
+// flat data-parallel pass over the node arrays (cycle discovery, leaving-arc arg-min, re-labelling,
+// potential update) instead of a pointer chase.  Only parent / pred / pred_dir / flow / state / pi are
+// semantically observable, and they are maintained exactly as the reference maintains them.
+#pragma once
+#include <stdint.h>
+
+namespace mcf {
+
+constexpr int kThreads = 1024;          // threads per CTA of the persistent pivot kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kListSmem = 3584;         // cycle entries staged in shared memory (32 B each = 112 KB)
+constexpr int kStemCap = 2048;          // longest stem (u_in .. u_out) handled by the in-kernel sort
+
+// SpanningTree.cs:53-71
+constexpr int STATE_UPPER = -1, STATE_TREE = 0, STATE_LOWER = 1;
+
+// SolverStatus.cs:7-34 (+ engine-internal codes >= 100 that the host turns into error returns)
+enum : int {
+    ST_NOT_SOLVED = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_UNBALANCED = 4,
+    ST_ERR_CYCLE_TOO_LONG = 100, ST_ERR_BARRIER_TIMEOUT = 101, ST_ERR_STEM_TOO_LONG = 102, ST_STOPPED_EARLY = 103
+};
+
+// pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599)
+enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3 };
+
+struct __align__(16) PriceRec {         // one pricing candidate (per CTA, per round)
+    long long c;                        // reduced cost (negative when valid, 0 = none)
+    int arc, src, tgt, cost;
+    int state, off;                     // off = scan offset from next_arc (Block/First)
+};
+
+struct __align__(16) CycEnt {           // one tree node of the pivot cycle, captured before any update
+    int u, in, sz, pd;                  // pd = pred_arc * 2 + (pred_dir == DIR_UP)
+    long long flow, d;                  // flow on pred arc, residual in cycle direction
+};
+
+struct Ctl {                            // control block in global memory (zeroed before launch)
+    unsigned long long bar;             // monotonically increasing grid-barrier counter
+    int abort;                          // set by a barrier time-out
+    int list_count[2];                  // cycle-list fill, double buffered by pivot parity
+    int status;
+    int final_block_size;
+    int infeasible;                     // CheckFeasibility, NS.cs:1272-1283
+    long long iterations;
+    long long arcs_checked;             // SolverMetrics.TotalArcsChecked
+    long long total_cost;               // GetTotalCost, NS.cs:452-465
+    long long degenerate;               // pivots with delta == 0
+    long long cycle_nodes;              // sum of cycle lengths (tree nodes)
+    long long moved_nodes;              // sum of re-hung subtree sizes
+    long long max_cycle, max_stem;
+    long long pricing_rounds;           // grid-wide pricing rounds (each = one barrier)
+    unsigned long long ns_price, ns_cycle, ns_update, ns_total;   // %globaltimer deltas seen by CTA 0
+};
+
+struct Params {
+    int n, m, S, A;                     // nodes, arcs, search arcs (m+n), allocated arcs
+    // arcs
+    const int* src; const int* tgt; const int* cost;     // [S]
+    int* state;                                          // [A]
+    long long* flow;                                     // [A]
+    const long long* upper;                              // [A]
+    const long long* orig_lower;                         // [m] or nullptr (restored into flow at the end)
+    long long* rc_cache;                                 // [S] or nullptr (PK_BLOCK_CACHED)
+    // nodes, [n+1] (root = n)
+    int* in; int* sz; int* parent; int* pd;
+    long long* pi;
+    // work areas
+    PriceRec* part;                     // [2][gridDim.x]
+    CycEnt* list; int list_cap;
+    Ctl* ctl;
+    // pricing configuration (BlockSearchPivot ctor, NS.cs:1304-1337; adaptive rule :1399-1438)
+    int kind;
+    int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
+    double low_thr, high_thr, shrink, grow;
+    int lookahead0;                     // groups priced in the first round of a search
+    long long max_iterations;           // NS.cs:280
+    long long stop_after;               // >0: stop after this many pivots (bounded samples / tests)
+    unsigned long long barrier_timeout_cycles;
+};
+
+}  // namespace mcf

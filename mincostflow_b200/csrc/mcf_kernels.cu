@@ -1,0 +1,618 @@
+// mcf_kernels.cu - the persistent cooperative pivot kernel of libmcfgpu (sm_100a).
+//
+// One launch runs the whole `while(true)` of NetworkSimplex.Solve() (NS.cs:282-341): no pivot ever returns
+// to the host.  Every pivot is three grid-wide phases separated by a hand-rolled grid barrier:
+//
+//   A  pricing      FindEnteringArc (NS.cs:1339-1441 Block Search, :1607-1636 First Eligible,
+//                   :1644-1667 Best Eligible, :1492-1598 cached Block Search): CTAs price whole blocks of the
+//                   cyclic scan (or, for Best Eligible, a coalesced 128-bit sweep of all S arcs), arg-min with
+//                   the reference's "first minimum in scan order" tie-break, one candidate per CTA.
+//   B  cycle        FindJoinNode + both walks of FindLeavingArc (NS.cs:925-1010) as ONE flat pass: node u is on
+//                   the cycle iff exactly one end of the entering arc lies in subtree(u) (interval test on
+//                   in[]/sz[]).  Cycle nodes are appended, with their residuals, to a list in global memory.
+//   C  update       every CTA reduces the (short) list redundantly -> leaving arc with the reference's
+//                   strict-< / <= tie rules, delta, stem.  CTA 0 applies ChangeFlow (NS.cs:1012-1040) and the
+//                   parent/pred/pred_dir/succ_num part of UpdateTreeStructure (NS.cs:1042-1183); all CTAs
+//                   re-label in[] in closed form and add sigma to pi over the re-hung subtree (NS.cs:1185-1209).
+//
+// Mutable arrays are read with ld.global.cg (L2) after each barrier; static arc arrays go through ld.global.nc.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include "mcf_device.cuh"
+
+namespace mcf {
+
+// ------------------------------------------------------------------------------------------------ helpers
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_inc_u64(unsigned long long* p)
+{
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct Key { long long a; int b; int idx; };            // lexicographic (a, b) minimum with a payload
+__device__ __forceinline__ bool key_less(const Key& x, const Key& y) { return x.a < y.a || (x.a == y.a && x.b < y.b); }
+__device__ __forceinline__ Key key_none() { Key k; k.a = LLONG_MAX; k.b = INT_MAX; k.idx = -1; return k; }
+
+__device__ __forceinline__ Key warp_min(Key k)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Key t;
+        t.a = __shfl_xor_sync(0xffffffffu, k.a, o);
+        t.b = __shfl_xor_sync(0xffffffffu, k.b, o);
+        t.idx = __shfl_xor_sync(0xffffffffu, k.idx, o);
+        if (key_less(t, k)) k = t;
+    }
+    return k;
+}
+
+__device__ Key block_min(Key k, Key* s_red)               // s_red[kWarps]; result broadcast to all threads
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    k = warp_min(k);
+    if (lane == 0) s_red[warp] = k;
+    __syncthreads();
+    if (warp == 0) {
+        k = lane < kWarps ? s_red[lane] : key_none();
+        k = warp_min(k);
+        if (lane == 0) s_red[0] = k;
+    }
+    __syncthreads();
+    k = s_red[0];
+    __syncthreads();
+    return k;
+}
+
+struct Shared {
+    Key red[2][kWarps];
+    PriceRec rec;                      // winning pricing candidate of this pivot
+    int found, abort, nstem;
+    int h_inF, h_inS;                  // in[first], in[second]
+    long long h_piF, h_piS, h_up, h_fl;
+    int st_u[kStemCap], st_in[kStemCap], st_z[kStemCap], st_pd[kStemCap];   // stem s_0 = u_in .. s_m = u_out
+    int tmp_idx[kStemCap];
+};
+
+// Grid barrier: one release-increment per CTA on a monotonically increasing counter, acquire-poll by thread 0.
+// Returns false when the solve must be abandoned (time-out: some CTA never arrived).
+__device__ bool grid_barrier(const Params& P, Shared& sh, unsigned long long& target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        red_release_inc_u64(&P.ctl->bar);
+        const long long t0 = clock64();
+        int ab = 0;
+        while (ld_acquire_u64(&P.ctl->bar) < target) {
+            if (*(volatile int*)&P.ctl->abort) { ab = 1; break; }
+            if ((unsigned long long)(clock64() - t0) > P.barrier_timeout_cycles) {
+                *(volatile int*)&P.ctl->abort = 1; ab = 1; break;
+            }
+        }
+        __threadfence();
+        sh.abort = ab;
+    }
+    __syncthreads();
+    return sh.abort == 0;
+}
+
+__device__ __forceinline__ long long reduced_cost(const Params& P, int e)
+{
+    const int s = __ldg(P.src + e), t = __ldg(P.tgt + e), c = __ldg(P.cost + e);
+    const int st = __ldcg(P.state + e);
+    return (long long)st * ((long long)c + __ldcg(P.pi + s) - __ldcg(P.pi + t));
+}
+
+// winner of this CTA -> part[buf][cta]
+__device__ __forceinline__ void publish_candidate(const Params& P, int buf, long long c, int arc, int off)
+{
+    PriceRec r;
+    r.c = c; r.arc = arc; r.off = off;
+    r.src = __ldg(P.src + arc); r.tgt = __ldg(P.tgt + arc); r.cost = __ldg(P.cost + arc);
+    r.state = __ldcg(P.state + arc);
+    P.part[(size_t)buf * gridDim.x + blockIdx.x] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+
+__global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    CycEnt* s_list = reinterpret_cast<CycEnt*>(dyn_smem);
+    __shared__ Shared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int n = P.n, S = P.S;
+    unsigned long long bar_target = 0;
+
+    // replicated (uniform) solver state
+    int next_arc = 0, B = P.block_size, cons_low = 0, cons_high = 0;
+    long long iterations = 0, arcs_checked = 0, degenerate = 0, cycle_nodes = 0, moved_nodes = 0;
+    long long max_cycle = 0, max_stem = 0, rounds_total = 0;
+    int price_buf = 0;                 // parity of the pricing round (double-buffers part[])
+    int cache_dirty = 1;               // _reducedCostsDirty, NS.cs:65
+    int status = ST_NOT_SOLVED;
+    unsigned long long t_price = 0, t_cycle = 0, t_update = 0, t_mark = 0, t_begin = 0;
+    if (cta == 0 && tid == 0) t_begin = t_mark = globaltimer_ns();
+
+    for (;;) {
+        // =============================================================== phase A: pricing
+        bool found = false;
+        int arcs_this = 0;
+        if (P.kind == PK_BLOCK_CACHED && cache_dirty) {
+            // UpdateReducedCosts "full update" arm, NS.cs:1251-1268: only arcs < min(S, m); [m, S) stay 0.
+            const int lim = S < P.m ? S : P.m;
+            for (int e = cta * kThreads + tid; e < lim; e += G * kThreads) {
+                const int st = __ldcg(P.state + e);
+                P.rc_cache[e] = st != STATE_TREE ? reduced_cost(P, e) : 0;
+            }
+            cache_dirty = 0;
+            if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        }
+        if (P.kind == PK_BLOCK || P.kind == PK_BLOCK_CACHED) {
+            long long groups_done = 0;
+            int L = P.lookahead0;
+            for (;;) {
+                const int nact = L < G ? L : G;
+                if (cta < nact) {
+                    const long long gi = groups_done + cta;
+                    const long long lo = gi * (long long)B;
+                    long long hi = lo + B; if (hi > S) hi = S;
+                    long long bestc = 0; int bestoff = INT_MAX;
+                    for (long long off = lo + tid; off < hi; off += kThreads) {
+                        int idx = next_arc + (int)off; if (idx >= S) idx -= S;
+                        const long long c = P.kind == PK_BLOCK ? reduced_cost(P, idx) : __ldcg(P.rc_cache + idx);
+                        if (c < bestc) { bestc = c; bestoff = (int)off; }
+                    }
+                    Key k; k.a = bestc; k.b = bestoff; k.idx = tid;
+                    k = block_min(k, sh.red[0]);
+                    if (k.a < 0) {
+                        if (k.idx == tid) { int idx = next_arc + k.b; if (idx >= S) idx -= S; publish_candidate(P, price_buf, k.a, idx, k.b); }
+                    } else if (tid == 0) {
+                        P.part[(size_t)price_buf * G + cta].c = 0;
+                    }
+                }
+                if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                rounds_total++;
+                if (warp == 0) {                    // first CTA (= first block in scan order) with a negative minimum
+                    int win = -1;
+                    for (int j0 = 0; j0 < nact && win < 0; j0 += 32) {
+                        const int j = j0 + lane;
+                        const long long c = j < nact ? __ldcg(&P.part[(size_t)price_buf * G + j].c) : 0;
+                        const unsigned mask = __ballot_sync(0xffffffffu, c < 0);
+                        if (mask) win = j0 + __ffs(mask) - 1;
+                    }
+                    if (lane == 0) {
+                        sh.found = win;
+                        if (win >= 0) {
+                            const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + win]);
+                            int4* d = reinterpret_cast<int4*>(&sh.rec);
+                            d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+                        }
+                    }
+                }
+                __syncthreads();
+                price_buf ^= 1;
+                const int win = sh.found;
+                if (win >= 0) {
+                    long long end = (groups_done + win + 1) * (long long)B; if (end > S) end = S;
+                    arcs_this = (int)end;
+                    // `_nextArc = e` (NS.cs:1397): the last arc examined, or unchanged after a full sweep without goto
+                    if (end < S || (long long)S % B == 0) { int e = next_arc + (int)end - 1; if (e >= S) e -= S; next_arc = e; }
+                    found = true;
+                    break;
+                }
+                groups_done += nact;
+                if (groups_done * (long long)B >= S) { arcs_this = S; break; }
+                L = L * 2 < G ? L * 2 : G;
+            }
+            if (status != ST_NOT_SOLVED) break;
+            arcs_checked += arcs_this;
+            if (found && P.adaptive) {              // NS.cs:1399-1438
+                const double hit = arcs_this > 0 ? 1.0 / arcs_this : 0;
+                if (hit < P.low_thr) {
+                    cons_high = 0; cons_low++;
+                    if (cons_low >= P.consecutive) { const int ns = (int)(B * P.shrink); B = P.dyn_min_block > ns ? P.dyn_min_block : ns; cons_low = 0; }
+                } else if (hit > P.high_thr) {
+                    cons_low = 0; cons_high++;
+                    if (cons_high >= P.consecutive) { const int ns = (int)(B * P.grow); B = P.max_block_size < ns ? P.max_block_size : ns; cons_high = 0; }
+                } else { cons_low = 0; cons_high = 0; }
+            }
+        } else if (P.kind == PK_FIRST) {
+            constexpr int K = 4;
+            long long done = 0;
+            int L = P.lookahead0;
+            for (;;) {
+                const int nact = L < G ? L : G;
+                if (cta < nact) {
+                    const long long lo = done + (long long)cta * kThreads * K;
+                    long long firstoff = LLONG_MAX, firstc = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const long long off = lo + (long long)k * kThreads + tid;
+                        if (off < S) {
+                            int idx = next_arc + (int)off; if (idx >= S) idx -= S;
+                            const long long c = reduced_cost(P, idx);
+                            if (c < 0 && off < firstoff) { firstoff = off; firstc = c; }
+                        }
+                    }
+                    Key k; k.a = firstoff; k.b = 0; k.idx = tid;
+                    k = block_min(k, sh.red[0]);
+                    if (k.a != LLONG_MAX) {
+                        if (k.idx == tid) { int idx = next_arc + (int)k.a; if (idx >= S) idx -= S; publish_candidate(P, price_buf, firstc, idx, (int)k.a); }
+                    } else if (tid == 0) {
+                        P.part[(size_t)price_buf * G + cta].c = 0;
+                    }
+                }
+                if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                rounds_total++;
+                if (warp == 0) {
+                    int win = -1;
+                    for (int j0 = 0; j0 < nact && win < 0; j0 += 32) {
+                        const int j = j0 + lane;
+                        const long long c = j < nact ? __ldcg(&P.part[(size_t)price_buf * G + j].c) : 0;
+                        const unsigned mask = __ballot_sync(0xffffffffu, c < 0);
+                        if (mask) win = j0 + __ffs(mask) - 1;
+                    }
+                    if (lane == 0) {
+                        sh.found = win;
+                        if (win >= 0) {
+                            const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + win]);
+                            int4* d = reinterpret_cast<int4*>(&sh.rec);
+                            d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+                        }
+                    }
+                }
+                __syncthreads();
+                price_buf ^= 1;
+                if (sh.found >= 0) { next_arc = sh.rec.arc + 1; found = true; break; }      // NS.cs:1617
+                done += (long long)nact * kThreads * K;
+                if (done >= S) break;
+                L = L * 2 < G ? L * 2 : G;
+            }
+            if (status != ST_NOT_SOLVED) break;
+        } else {  // PK_BEST: coalesced 128-bit sweep over all S arcs, lowest arc id wins ties (NS.cs:1649-1658)
+            Key best; best.a = 0; best.b = INT_MAX; best.idx = -1;
+            const int nquad = S >> 2;
+            const int4* src4 = reinterpret_cast<const int4*>(P.src);
+            const int4* tgt4 = reinterpret_cast<const int4*>(P.tgt);
+            const int4* cost4 = reinterpret_cast<const int4*>(P.cost);
+            const int4* st4 = reinterpret_cast<const int4*>(P.state);
+            for (int q = cta * kThreads + tid; q < nquad; q += G * kThreads) {
+                const int4 s = __ldg(src4 + q), t = __ldg(tgt4 + q), c = __ldg(cost4 + q), st = __ldcg(st4 + q);
+                const long long ps0 = __ldcg(P.pi + s.x), ps1 = __ldcg(P.pi + s.y), ps2 = __ldcg(P.pi + s.z), ps3 = __ldcg(P.pi + s.w);
+                const long long pt0 = __ldcg(P.pi + t.x), pt1 = __ldcg(P.pi + t.y), pt2 = __ldcg(P.pi + t.z), pt3 = __ldcg(P.pi + t.w);
+                const long long r0 = (long long)st.x * ((long long)c.x + ps0 - pt0);
+                const long long r1 = (long long)st.y * ((long long)c.y + ps1 - pt1);
+                const long long r2 = (long long)st.z * ((long long)c.z + ps2 - pt2);
+                const long long r3 = (long long)st.w * ((long long)c.w + ps3 - pt3);
+                const int e = q << 2;
+                if (r0 < best.a) { best.a = r0; best.b = e; }
+                if (r1 < best.a) { best.a = r1; best.b = e + 1; }
+                if (r2 < best.a) { best.a = r2; best.b = e + 2; }
+                if (r3 < best.a) { best.a = r3; best.b = e + 3; }
+            }
+            for (int e = (nquad << 2) + cta * kThreads + tid; e < S; e += G * kThreads) {
+                const long long r = reduced_cost(P, e);
+                if (r < best.a) { best.a = r; best.b = e; }
+            }
+            best.idx = tid;
+            best = block_min(best, sh.red[0]);
+            if (best.a < 0) { if (best.idx == tid) publish_candidate(P, price_buf, best.a, best.b, 0); }
+            else if (tid == 0) { P.part[(size_t)price_buf * G + cta].c = 0; P.part[(size_t)price_buf * G + cta].arc = INT_MAX; }
+            if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            rounds_total++;
+            if (warp == 0) {
+                Key k = key_none(); k.a = 0;
+                for (int j = lane; j < G; j += 32) {
+                    Key t; t.a = __ldcg(&P.part[(size_t)price_buf * G + j].c); t.b = __ldcg(&P.part[(size_t)price_buf * G + j].arc); t.idx = j;
+                    if (t.a < 0 && key_less(t, k)) k = t;
+                }
+                k = warp_min(k);
+                if (lane == 0) {
+                    sh.found = k.a < 0 ? k.idx : -1;
+                    if (k.a < 0) {
+                        const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + k.idx]);
+                        int4* d = reinterpret_cast<int4*>(&sh.rec);
+                        d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+                    }
+                }
+            }
+            __syncthreads();
+            price_buf ^= 1;
+            found = sh.found >= 0;
+        }
+        if (cta == 0 && tid == 0) { const unsigned long long t = globaltimer_ns(); t_price += t - t_mark; t_mark = t; }
+        if (!found) { status = ST_OPTIMAL; break; }      // feasibility is decided in the epilogue
+
+        iterations++;
+        if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }      // NS.cs:311-317
+        const int par = (int)(iterations & 1);
+
+        // =============================================================== phase B: cycle discovery
+        const int in_arc = sh.rec.arc, a_src = sh.rec.src, a_tgt = sh.rec.tgt, a_state = sh.rec.state, a_cost = sh.rec.cost;
+        const int first = a_state == STATE_LOWER ? a_src : a_tgt;      // NS.cs:948-957
+        const int second = a_state == STATE_LOWER ? a_tgt : a_src;
+        if (tid == 0) sh.h_inF = __ldcg(P.in + first);
+        if (tid == 1) sh.h_inS = __ldcg(P.in + second);
+        if (tid == 2) sh.h_piF = __ldcg(P.pi + first);
+        if (tid == 3) sh.h_piS = __ldcg(P.pi + second);
+        if (tid == 4) sh.h_up = __ldg(P.upper + in_arc);
+        if (tid == 5) sh.h_fl = __ldcg(P.flow + in_arc);
+        __syncthreads();
+        const int inF = sh.h_inF, inS = sh.h_inS;
+        for (int u = cta * kThreads + tid; u < n; u += G * kThreads) {
+            const int in_u = __ldcg(P.in + u), sz_u = __ldcg(P.sz + u);
+            const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
+            const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
+            if (hasF != hasS) {
+                const int pd = __ldcg(P.pd + u);
+                const int e = pd >> 1;
+                const long long fl = __ldcg(P.flow + e), up = __ldg(P.upper + e);
+                const long long res = up == LLONG_MAX ? (LLONG_MAX / 2) : up - fl;      // NS.cs:970-971
+                const bool dir_up = pd & 1;
+                // first side: residual when pred_dir == DOWN; second side: when pred_dir == UP (NS.cs:968, :986)
+                const long long d = (hasF ? !dir_up : dir_up) ? res : fl;
+                const int slot = atomicAdd(&P.ctl->list_count[par], 1);
+                if (slot < P.list_cap) {
+                    CycEnt ce; ce.u = u; ce.in = in_u; ce.sz = sz_u; ce.pd = pd; ce.flow = fl; ce.d = d;
+                    P.list[slot] = ce;
+                }
+            }
+        }
+        if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        if (cta == 0 && tid == 0) { const unsigned long long t = globaltimer_ns(); t_cycle += t - t_mark; t_mark = t; }
+
+        // =============================================================== phase C: leaving arc + updates
+        const int cnt = __ldcg(&P.ctl->list_count[par]);
+        if (cnt > kListSmem || cnt > P.list_cap) { status = ST_ERR_CYCLE_TOO_LONG; break; }
+        for (int t = tid; t < cnt; t += kThreads) {
+            const int4* q = reinterpret_cast<const int4*>(P.list + t);
+            int4* d = reinterpret_cast<int4*>(s_list + t);
+            d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+        }
+        if (cta == 0 && tid == 0) P.ctl->list_count[par ^ 1] = 0;       // next pivot's counter
+        __syncthreads();
+        Key k1 = key_none(), k2 = key_none();
+        for (int t = tid; t < cnt; t += kThreads) {
+            const CycEnt& ce = s_list[t];
+            const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
+            Key k; k.a = ce.d; k.idx = t;
+            if (side1) { k.b = -ce.in; if (key_less(k, k1)) k1 = k; }      // strict '<' from `first` upward: deepest minimum
+            else       { k.b = ce.in;  if (key_less(k, k2)) k2 = k; }      // '<=' from `second` upward: shallowest minimum
+        }
+        k1 = block_min(k1, sh.red[0]);
+        k2 = block_min(k2, sh.red[1]);
+        long long delta = sh.h_up;                                          // NS.cs:958
+        int result = 0, out_idx = -1;
+        if (k1.idx >= 0 && k1.a < delta) { delta = k1.a; result = 1; out_idx = k1.idx; }
+        if (k2.idx >= 0 && k2.a <= delta) { delta = k2.a; result = 2; out_idx = k2.idx; }
+        const bool change = result != 0;
+        if (!change && delta == 0) { status = ST_UNBOUNDED; break; }        // NS.cs:321-325
+        if (delta == 0) degenerate++;
+        cycle_nodes += cnt; if (cnt > max_cycle) max_cycle = cnt;
+
+        const int u_in = result == 1 ? first : second, v_in = result == 1 ? second : first;   // NS.cs:999-1008
+        const long long val = (long long)a_state * delta;                   // NS.cs:1017
+        const int src_side1 = a_state == STATE_LOWER;                       // is `first` the source of the entering arc?
+
+        // ---- ChangeFlow (CTA 0), NS.cs:1012-1040
+        if (cta == 0) {
+            if (delta > 0) {
+                if (tid == 0) P.flow[in_arc] = sh.h_fl + val;
+                for (int t = tid; t < cnt; t += kThreads) {
+                    const CycEnt& ce = s_list[t];
+                    const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
+                    const bool on_src_side = side1 == (bool)src_side1;
+                    const long long dv = (ce.pd & 1) ? val : -val;          // pred_dir * val
+                    P.flow[ce.pd >> 1] = on_src_side ? ce.flow - dv : ce.flow + dv;
+                }
+            }
+            if (tid == 0) {
+                if (change) {
+                    P.state[in_arc] = STATE_TREE;
+                    const CycEnt& ce = s_list[out_idx];
+                    const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
+                    const bool on_src_side = side1 == (bool)src_side1;
+                    const long long dv = (ce.pd & 1) ? val : -val;
+                    const long long nf = delta > 0 ? (on_src_side ? ce.flow - dv : ce.flow + dv) : ce.flow;
+                    P.state[ce.pd >> 1] = nf == 0 ? STATE_LOWER : STATE_UPPER;
+                } else {
+                    P.state[in_arc] = -a_state;
+                }
+            }
+        }
+
+        if (change) {
+            // ---- stem = cycle nodes on u_in's side from u_in up to u_out, deepest first
+            const CycEnt out = s_list[out_idx];
+            const int a = out.in, s = out.sz;                               // old interval of the re-hung subtree
+            const bool in_side1 = result == 1;
+            if (tid == 0) sh.nstem = 0;
+            __syncthreads();
+            for (int t = tid; t < cnt; t += kThreads) {
+                const CycEnt& ce = s_list[t];
+                const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
+                if (side1 == in_side1 && ce.in >= a) {
+                    const int p = atomicAdd(&sh.nstem, 1);
+                    if (p < kStemCap) sh.tmp_idx[p] = t;
+                }
+            }
+            __syncthreads();
+            const int ns = sh.nstem;
+            if (ns > kStemCap) { status = ST_ERR_STEM_TOO_LONG; break; }
+            for (int p = tid; p < ns; p += kThreads) {                      // rank by counting (in[] values are distinct)
+                const CycEnt& ce = s_list[sh.tmp_idx[p]];
+                int rank = 0;
+                for (int q = 0; q < ns; ++q) rank += s_list[sh.tmp_idx[q]].in > ce.in;
+                sh.st_u[rank] = ce.u; sh.st_in[rank] = ce.in; sh.st_z[rank] = ce.sz; sh.st_pd[rank] = ce.pd;
+            }
+            __syncthreads();
+            if (ns > max_stem) max_stem = ns;
+            moved_nodes += s;
+
+            const int b = result == 1 ? inS : inF;                          // in[v_in]
+            const int base = b < a ? b + 1 : b - s + 1;                     // new position of u_in (first child of v_in)
+            const int dir_new_up = u_in == a_src;                           // NS.cs:1143
+            const long long piU = result == 1 ? sh.h_piF : sh.h_piS, piV = result == 1 ? sh.h_piS : sh.h_piF;
+            const long long sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);   // NS.cs:1187-1188
+
+            // ---- parent / pred / pred_dir / succ_num of the stem and succ_num along both paths (CTA 0)
+            if (cta == 0) {
+                for (int k = tid; k < ns; k += kThreads) {
+                    const int u = sh.st_u[k];
+                    if (k == 0) { P.parent[u] = v_in; P.pd[u] = in_arc * 2 + dir_new_up; P.sz[u] = s; }
+                    else { P.parent[u] = sh.st_u[k - 1]; P.pd[u] = sh.st_pd[k - 1] ^ 1; P.sz[u] = s - sh.st_z[k - 1]; }
+                }
+                for (int t = tid; t < cnt; t += kThreads) {
+                    const CycEnt& ce = s_list[t];
+                    const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
+                    if (side1 != in_side1) P.sz[ce.u] = ce.sz + s;          // v_in .. join (NS.cs:1174-1177)
+                    else if (ce.in < a) P.sz[ce.u] = ce.sz - s;             // v_out .. join (NS.cs:1179-1182)
+                }
+            }
+
+            // ---- re-label in[] in closed form and add sigma over the re-hung subtree (all CTAs)
+            for (int u = cta * kThreads + tid; u < n; u += G * kThreads) {
+                const int x = __ldcg(P.in + u);
+                if ((unsigned)(x - a) < (unsigned)s) {
+                    int lo = 0, hi = ns - 1;                                // smallest k with x in [st_in[k], st_in[k]+st_z[k])
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((unsigned)(x - sh.st_in[mid]) < (unsigned)sh.st_z[mid]) hi = mid; else lo = mid + 1;
+                    }
+                    int off;
+                    if (lo == 0) off = x - sh.st_in[0];
+                    else {
+                        int r = x - sh.st_in[lo];
+                        if (x > sh.st_in[lo - 1]) r -= sh.st_z[lo - 1];
+                        off = sh.st_z[lo - 1] + r;
+                    }
+                    P.in[u] = base + off;
+                    P.pi[u] = __ldcg(P.pi + u) + sigma;
+                } else if (b < a) {
+                    if (x > b && x < a) P.in[u] = x + s;
+                } else {
+                    if (x >= a + s && x <= b) P.in[u] = x - s;
+                }
+            }
+            cache_dirty = 1;                                                // NS.cs:1205-1208
+        }
+        if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        if (cta == 0 && tid == 0) { const unsigned long long t = globaltimer_ns(); t_update += t - t_mark; t_mark = t; }
+        if (P.stop_after > 0 && iterations >= P.stop_after) { status = ST_STOPPED_EARLY; break; }
+    }
+
+    // =============================================================== epilogue
+    // An error/abort status is uniform across CTAs except for a barrier time-out, where CTAs may disagree on
+    // where they stopped; nothing below waits on another CTA in that case.
+    if (status == ST_OPTIMAL) {
+        // CheckFeasibility (NS.cs:1272-1283): arcs [m, m+n); GetTotalCost (NS.cs:452-465) over [0, m)
+        int bad = 0;
+        for (int e = P.m + cta * kThreads + tid; e < S; e += G * kThreads) bad |= __ldcg(P.flow + e) != 0;
+        if (bad) atomicOr(&P.ctl->infeasible, 1);
+        long long acc = 0;
+        for (int e = cta * kThreads + tid; e < P.m; e += G * kThreads) {
+            long long f = __ldcg(P.flow + e);
+            if (P.orig_lower) { const long long l = __ldg(P.orig_lower + e); if (l != 0) { f += l; P.flow[e] = f; } }   // NS.cs:375-388
+            acc += f * (long long)__ldg(P.cost + e);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&P.ctl->total_cost), (unsigned long long)acc);
+    }
+    if (cta == 0 && tid == 0) {
+        Ctl* c = P.ctl;
+        c->status = status; c->iterations = iterations; c->arcs_checked = arcs_checked; c->final_block_size = B;
+        c->degenerate = degenerate; c->cycle_nodes = cycle_nodes; c->moved_nodes = moved_nodes;
+        c->max_cycle = max_cycle; c->max_stem = max_stem; c->pricing_rounds = rounds_total;
+        c->ns_price = t_price; c->ns_cycle = t_cycle; c->ns_update = t_update; c->ns_total = globaltimer_ns() - t_begin;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone Best Eligible pricing sweep: the HBM-roofline kernel (16 B of arc data per arc priced), same inner
+// loop as phase A / PK_BEST above.  Used by mcf_pricing_probe() so the sweep can be timed with CUDA events and
+// captured by ncu in isolation; out[0..gridDim.x) receives one candidate per CTA.
+__global__ void __launch_bounds__(kThreads, 1) ns_price_sweep_kernel(const Params P, PriceRec* out)
+{
+    __shared__ Key red[kWarps];
+    const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x, S = P.S;
+    Key best; best.a = 0; best.b = INT_MAX; best.idx = -1;
+    const int nquad = S >> 2;
+    const int4* src4 = reinterpret_cast<const int4*>(P.src);
+    const int4* tgt4 = reinterpret_cast<const int4*>(P.tgt);
+    const int4* cost4 = reinterpret_cast<const int4*>(P.cost);
+    const int4* st4 = reinterpret_cast<const int4*>(P.state);
+    for (int q = cta * kThreads + tid; q < nquad; q += G * kThreads) {
+        const int4 s = __ldg(src4 + q), t = __ldg(tgt4 + q), c = __ldg(cost4 + q), st = __ldcg(st4 + q);
+        const long long ps0 = __ldcg(P.pi + s.x), ps1 = __ldcg(P.pi + s.y), ps2 = __ldcg(P.pi + s.z), ps3 = __ldcg(P.pi + s.w);
+        const long long pt0 = __ldcg(P.pi + t.x), pt1 = __ldcg(P.pi + t.y), pt2 = __ldcg(P.pi + t.z), pt3 = __ldcg(P.pi + t.w);
+        const long long r0 = (long long)st.x * ((long long)c.x + ps0 - pt0);
+        const long long r1 = (long long)st.y * ((long long)c.y + ps1 - pt1);
+        const long long r2 = (long long)st.z * ((long long)c.z + ps2 - pt2);
+        const long long r3 = (long long)st.w * ((long long)c.w + ps3 - pt3);
+        const int e = q << 2;
+        if (r0 < best.a) { best.a = r0; best.b = e; }
+        if (r1 < best.a) { best.a = r1; best.b = e + 1; }
+        if (r2 < best.a) { best.a = r2; best.b = e + 2; }
+        if (r3 < best.a) { best.a = r3; best.b = e + 3; }
+    }
+    for (int e = (nquad << 2) + cta * kThreads + tid; e < S; e += G * kThreads) {
+        const long long r = reduced_cost(P, e);
+        if (r < best.a) { best.a = r; best.b = e; }
+    }
+    best.idx = tid;
+    best = block_min(best, red);
+    if (tid == 0) { PriceRec r; r.c = best.a; r.arc = best.a < 0 ? best.b : -1; r.src = r.tgt = r.cost = r.state = r.off = 0; out[cta] = r; }
+}
+
+}  // namespace mcf
+
+// ------------------------------------------------------------------------------------------------ launchers
+
+extern "C" int mcfk_pivot_smem_bytes() { return mcf::kListSmem * (int)sizeof(mcf::CycEnt); }
+
+extern "C" int mcfk_max_grid(int device, int* sm_count)
+{
+    int dev = device, sms = 0, per_sm = 0;
+    if (cudaGetDeviceCount(&sms) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    const int smem = mcfk_pivot_smem_bytes();
+    if (cudaFuncSetAttribute(mcf::ns_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcf::ns_pivot_kernel, mcf::kThreads, smem) != cudaSuccess) return -3;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return per_sm * prop.multiProcessorCount;
+}
+
+extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream)
+{
+    const int smem = mcfk_pivot_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(mcf::ns_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    void* args[] = {(void*)p};
+    e = cudaLaunchCooperativeKernel((const void*)mcf::ns_pivot_kernel, dim3(grid), dim3(mcf::kThreads), args, smem, stream);
+    return (int)e;
+}
+
+extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream)
+{
+    mcf::ns_price_sweep_kernel<<<grid, mcf::kThreads, 0, stream>>>(*p, out);
+    return (int)cudaGetLastError();
+}
