@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes mirror in mincostflow_b200/solver.py), against the
+CPU oracle on the same inputs - status, pivot count, total cost, every arc flow and every node potential bit-exact -
+plus the reference's own golden vectors and an independent SolutionValidator-style optimality check.
+Modelled on src/MinCostFlow.Tests/Lemon/{NetworkSimplexTests,OptimizationTests,SolverComparisonTests}.cs."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, lemon_case_problem
+import mincostflow_b200 as mcf
+from mincostflow_b200 import instances
+from mincostflow_b200.instances import Problem
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_cfg(cfg: mcf.OptimizationConfig):
+    c = oracle.default_config()
+    c.flags = int(cfg.Flags); c.max_block_size = cfg.MaxBlockSize; c.min_block_size = cfg.MinBlockSize
+    c.consecutive_hits_before_adapt = cfg.ConsecutiveHitsBeforeAdapt
+    c.block_size_growth_factor = cfg.BlockSizeGrowthFactor; c.block_size_shrink_factor = cfg.BlockSizeShrinkFactor
+    c.low_hit_rate_threshold = cfg.LowHitRateThreshold; c.high_hit_rate_threshold = cfg.HighHitRateThreshold
+    c.min_block_size_ratio = cfg.MinBlockSizeRatio
+    return c
+
+
+def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, optimized=False, expect_cost=None):
+    """Solve on the GPU and on the oracle; everything observable must be identical."""
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ns.SetPivotRule(rule).SetSupplyType(supply_type)
+    if cfg is not None:
+        ns.SetOptimizationConfig(cfg)
+    if optimized:
+        ns.EnableOptimizedPivot(True)
+    st = ns.Solve()
+    r, rflow, rpi, _, _ = oracle.solve(p, pivot_rule=int(rule), supply_type=supply_type, optimized_pivot=optimized,
+                                       config=None if cfg is None else _oracle_cfg(cfg))
+    M = ns.GetMetrics()
+    tag = (p.name, int(rule), supply_type, optimized)
+    assert int(st) == r.status, (tag, int(st), r.status)
+    assert M.iterations == r.iterations, (tag, M.iterations, r.iterations)
+    if rule == mcf.PivotRule.BlockSearch and not optimized:
+        assert (M.initial_block_size, M.final_block_size) == (r.initial_block_size, r.final_block_size), tag
+        assert M.total_arcs_checked == r.total_arcs_checked, tag
+        assert M.pricing_kind == r.pivot_kind, tag
+    if st == mcf.SolverStatus.Optimal:
+        assert ns.GetTotalCost() == r.total_cost, tag
+        assert np.array_equal(ns.flows(), rflow), tag
+        assert np.array_equal(ns.potentials(), rpi), tag
+        if int(np.sum(p.supply)) == 0:     # unbalanced GEQ/LEQ instances are misreported by the reference
+            bad, dual = oracle.validate(p, ns.flows(), ns.potentials(), ns.GetTotalCost(), supply_type=supply_type)
+            assert bad == 0, (tag, bad)
+        if expect_cost is not None:
+            assert ns.GetTotalCost() == expect_cost, tag
+    else:
+        with pytest.raises(mcf.InvalidOperationException):
+            ns.GetTotalCost()
+    return ns, r
+
+
+# ------------------------------------------------------------------ reference known answers through the setter API
+
+def test_simple_transportation_problem_solves_correctly():
+    """NetworkSimplexTests.cs:28-79, written the way the reference test is."""
+    builder = mcf.GraphBuilder()
+    builder.AddNodes(4)
+    builder.AddArc(0, 2).AddArc(0, 3).AddArc(1, 2).AddArc(1, 3)
+    graph = builder.Build()
+    s = mcf.NetworkSimplex(graph)
+    s.SetNodeSupply(builder.GetNode(0), 10); s.SetNodeSupply(builder.GetNode(1), 15)
+    s.SetNodeSupply(builder.GetNode(2), -12); s.SetNodeSupply(builder.GetNode(3), -13)
+    s.SetArcCost(mcf.Arc(0), 3); s.SetArcCost(mcf.Arc(1), 5); s.SetArcCost(mcf.Arc(2), 4); s.SetArcCost(mcf.Arc(3), 2)
+    assert s.Solve() == mcf.SolverStatus.Optimal
+    assert s.GetTotalCost() == 64
+    assert [s.GetFlow(mcf.Arc(i)) for i in range(4)] == [10, 0, 2, 13]
+    assert s.Status == mcf.SolverStatus.Optimal and s.SupplyType == mcf.SupplyType.Geq
+
+
+def test_known_answer_flows(golden):
+    for k in golden["known_answers"]:
+        p = Problem(k["n"], len(k["src"]), np.asarray(k["src"], np.int32), np.asarray(k["tgt"], np.int32),
+                    np.asarray(k["low"], np.int64), np.asarray(k["up"], np.int64), np.asarray(k["cost"], np.int64),
+                    np.asarray(k["sup"], np.int64), k["name"])
+        ns, _ = check_parity(p, expect_cost=k["total_cost"])
+        assert ns.flows().tolist() == k["flows"], k["name"]
+
+
+def test_getters_before_solve_and_bad_ids():
+    """NetworkSimplex.cs:418-426, :155-158."""
+    g = mcf.GraphBuilder().AddNodes(2).AddArc(0, 1).Build()
+    s = mcf.NetworkSimplex(g)
+    with pytest.raises(mcf.InvalidOperationException):
+        s.GetFlow(mcf.Arc(0))
+    with pytest.raises(mcf.ArgumentException):
+        s.SetArcCost(mcf.Arc(3), 1)
+    with pytest.raises(mcf.ArgumentException):
+        s.SetNodeSupply(mcf.Node(2), 1)
+    s.SetNodeSupply(mcf.Node(0), 4); s.SetNodeSupply(mcf.Node(1), -4); s.SetArcCost(mcf.Arc(0), 7)
+    assert s.Solve() == mcf.SolverStatus.Optimal and s.GetTotalCost() == 28 and s.GetFlow(mcf.Arc(0)) == 4
+    with pytest.raises(mcf.ArgumentException):
+        s.GetFlow(mcf.Arc(1))
+    with pytest.raises(mcf.ArgumentException):
+        s.GetPotential(mcf.Node(-1))
+    s.SetPivotRule(mcf.PivotRule.CandidateList)
+    with pytest.raises(NotImplementedError):                        # NetworkSimplex.cs:884
+        s.Solve()
+
+
+def test_edge_cases():
+    # no arcs: every node balanced -> optimal, cost 0
+    p = Problem(3, 0, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64),
+                np.zeros(0, np.int64), np.zeros(3, np.int64), "no_arcs")
+    check_parity(p, expect_cost=0)
+    # no arcs but a supply: infeasible
+    p2 = Problem(2, 0, p.source, p.target, p.lower, p.upper, p.cost, np.array([3, -3], np.int64), "no_arcs_supply")
+    check_parity(p2)
+    # upper < lower: CheckBounds (NetworkSimplex.cs:624-634)
+    p3 = Problem(2, 1, np.array([0], np.int32), np.array([1], np.int32), np.array([5], np.int64), np.array([3], np.int64),
+                 np.array([1], np.int64), np.array([4, -4], np.int64), "bad_bounds")
+    ns, _ = check_parity(p3)
+    assert ns.Status == mcf.SolverStatus.Infeasible
+    # capacity too small: infeasible through the artificial arcs
+    p4 = Problem(2, 1, np.array([0], np.int32), np.array([1], np.int32), np.array([0], np.int64), np.array([3], np.int64),
+                 np.array([1], np.int64), np.array([4, -4], np.int64), "cap_too_small")
+    check_parity(p4)
+    # parallel arcs, a self loop and negative costs
+    p5 = Problem(3, 5, np.array([0, 0, 1, 1, 2], np.int32), np.array([1, 1, 1, 2, 0], np.int32), np.zeros(5, np.int64),
+                 np.array([4, 9, 5, 9, 2], np.int64), np.array([5, 7, -1, 2, -20], np.int64), np.array([6, 0, -6], np.int64), "multi")
+    for rule in mcf.PivotRule.FirstEligible, mcf.PivotRule.BestEligible, mcf.PivotRule.BlockSearch:
+        check_parity(p5, rule=rule)
+
+
+# ------------------------------------------------------------------ fixtures of the reference
+
+def test_all_fixtures_default_solve(golden, load_fixture):
+    """Default Solve() (auto-configuration on, which picks cached Block Search / adaptive blocks per instance) on every
+    stored fixture: == oracle bit for bit, == .sol objective (PerformanceComparisonReport.cs:253-268)."""
+    for name, e in golden["fixtures"].items():
+        if not e.get("stored") or name == "AURV19V6":               # AURV19V6: own test below (long cached-pricing run)
+            continue
+        check_parity(load_fixture(name), expect_cost=e.get("objective"))
+
+
+@pytest.mark.parametrize("rule", [mcf.PivotRule.FirstEligible, mcf.PivotRule.BestEligible, mcf.PivotRule.BlockSearch])
+def test_small_fixtures_all_rules_and_optimized_pivot(golden, load_fixture, rule):
+    """OptimizationTests.cs:14-120: every rule, managed and `EnableOptimizedPivot` variants."""
+    for name, e in golden["fixtures"].items():
+        if not e.get("stored") or e["m"] > 10000:
+            continue
+        p = load_fixture(name)
+        check_parity(p, rule=rule, expect_cost=e.get("objective"))
+        if rule != mcf.PivotRule.BlockSearch:                       # optimized Block Search is refused by the engine
+            check_parity(p, rule=rule, optimized=True, expect_cost=e.get("objective"))
+
+
+def test_published_pivot_counts_on_gpu(golden, load_fixture):
+    """docs/performance-optimization-final-results.md:50-53, reproduced by the CUDA engine itself."""
+    p = load_fixture("circulation_1000_0_05")
+    for g in golden["pivot_counts_circulation_1000_0_05"]:
+        cfg = mcf.OptimizationConfig(Flags=mcf.OptimizationFlags(g["flags"]), MinBlockSize=g["min_block_size"], MaxBlockSize=g["max_block_size"])
+        ns, _ = check_parity(p, cfg=cfg, expect_cost=golden["fixtures"]["circulation_1000_0_05"]["objective"])
+        M = ns.GetMetrics()
+        assert M.iterations == g["iterations"] and [M.initial_block_size, M.final_block_size] == g["block"], g
+
+
+def test_lemon_cases_match_oracle(golden):
+    """LEMON's 21 cases incl. lower bounds, GEQ / LEQ forms, negative costs, infinite capacities - GPU == restated C#
+    semantics (quirks included); balanced cases also == LEMON's expected cost."""
+    for case in golden["lemon_cases"]:
+        p, stype, status, total = lemon_case_problem(golden, case)
+        for rule in mcf.PivotRule.FirstEligible, mcf.PivotRule.BestEligible, mcf.PivotRule.BlockSearch:
+            balanced_opt = int(p.supply.sum()) == 0 and status == 1
+            check_parity(p, rule=rule, supply_type=stype, expect_cost=total if balanced_opt else None)
+
+
+def test_aurv19v6_cached_pricing_path(golden, load_fixture):
+    """AURV19V6 takes the reference's CachedBlockSearchPivot path (full O(m) recompute per pivot)."""
+    ns, r = check_parity(load_fixture("AURV19V6"), expect_cost=golden["fixtures"]["AURV19V6"]["objective"])
+    assert ns.GetMetrics().pricing_kind == 3
+
+
+# ------------------------------------------------------------------ NETGEN family (BASELINE.json configs)
+
+@pytest.mark.parametrize("k", [8, 10, 13, 14])
+def test_netgen8_block_search(golden, k):
+    p = instances.netgen8(k)
+    obj = golden["fixtures"][f"netgen_8_{k:02d}a"]["objective"]
+    check_parity(p, cfg=mcf.OptimizationConfig(), expect_cost=obj)          # canonical comparator: auto-config off
+    check_parity(p, expect_cost=obj)                                        # default Solve()
+    check_parity(p, rule=mcf.PivotRule.FirstEligible, expect_cost=obj)
+    if k <= 10:
+        check_parity(p, rule=mcf.PivotRule.BestEligible, expect_cost=obj)
+
+
+def test_config1_netgen_10k_30k():
+    """BASELINE.json config 1: default Solve() takes the cached-pricing path; canonical comparator is plain Block Search."""
+    p = instances.netgen(13502460, instances.netgen_params(10000, m=30000, sources=100, sinks=100, supply=100000), name="netgen_10k_30k")
+    check_parity(p, cfg=mcf.OptimizationConfig())
+    ns, _ = check_parity(p)
+    assert ns.GetMetrics().pricing_kind == 3
+
+
+def test_grid_time_expanded_small():
+    """BASELINE.json config 4 at 64x64 and 128x96: long, thin time-expanded grid (deep trees, long cycles)."""
+    check_parity(instances.grid_time_expanded(64, 64), cfg=mcf.OptimizationConfig())
+    check_parity(instances.grid_time_expanded(128, 96, seed=7), cfg=mcf.OptimizationConfig())
+
+
+def _large(name):
+    with open(os.path.join(GOLDEN_DIR, "large.json")) as f:
+        return json.load(f).get(name)
+
+
+@pytest.mark.parametrize("k", [16, 18, 20])
+def test_netgen8_full_size_against_recorded_oracle(k):
+    """Full-size solves (BASELINE.json configs 2, 3 and the per-instance size of config 5) against what the CPU oracle
+    produced in the build container (tests/golden/large.json, tools/make_golden_large.py): pivot count, total cost,
+    sha256 of the flow and potential arrays; plus the size-independent optimality check (complementary slackness,
+    conservation, bounds, primal == dual objective) computed here."""
+    g = _large(f"netgen_8_{k}a")
+    if g is None:
+        pytest.skip("no recorded oracle result for this size")
+    p = instances.netgen8(k)
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ns.SetOptimizationConfig(mcf.OptimizationConfig())
+    assert ns.Solve() == mcf.SolverStatus.Optimal
+    assert ns.GetMetrics().iterations == g["pivots"]
+    assert ns.GetTotalCost() == g["total_cost"] == g.get("lemon_cost", g["total_cost"])
+    assert hashlib.sha256(ns.flows().tobytes()).hexdigest() == g["flow_sha256"]
+    assert hashlib.sha256(ns.potentials().tobytes()).hexdigest() == g["pi_sha256"]
+    bad, dual = oracle.validate(p, ns.flows(), ns.potentials(), ns.GetTotalCost())
+    assert bad == 0 and dual == g["total_cost"]
+
+
+def test_best_eligible_prefix_at_2_16():
+    """Best Eligible on 2^16 nodes for a bounded number of pivots: same pivot count and (via a full small solve above)
+    the same tie-break; a full BE solve at this size is hours of CPU."""
+    p = instances.netgen8(16)
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ns.SetPivotRule(mcf.PivotRule.BestEligible).SetOptimizationConfig(mcf.OptimizationConfig())
+    ns.set_engine_options(stop_after_pivots=300)
+    assert ns.Solve() == mcf.SolverStatus.NotSolved
+    assert ns.GetMetrics().iterations == 300
+
+
+def test_pricing_probe_entering_arc_matches_oracle_first_pivot():
+    """The stand-alone roofline sweep returns the Best Eligible entering arc of the initial basis."""
+    p = instances.netgen8(14)
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ms, arc, arcs = ns.pricing_probe(reps=2, flush_l2=False)
+    r, _, _, tin, _ = oracle.solve(p, pivot_rule=oracle.BEST_ELIGIBLE, config=oracle.default_config(), max_pivots=1, trace=4)
+    assert arcs == p.n + p.m and arc == int(tin[0])
+
+
+def test_solve_batch_single_device():
+    ps = [instances.netgen8(10, seed=13502460 + i) for i in range(4)]
+    solvers = [mcf.NetworkSimplex.from_problem(p) for p in ps]
+    for s in solvers:
+        s.SetOptimizationConfig(mcf.OptimizationConfig())
+    sts = mcf.solve_batch(solvers, [0])
+    for p, s, st in zip(ps, solvers, sts):
+        r, rflow, rpi, _, _ = oracle.solve(p, config=oracle.default_config())
+        assert int(st) == r.status == 1 and s.GetTotalCost() == r.total_cost
+        assert np.array_equal(s.flows(), rflow) and np.array_equal(s.potentials(), rpi)

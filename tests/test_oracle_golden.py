@@ -1,0 +1,165 @@
+"""Pins the CPU oracle (oracle/ns_oracle.c) to everything the reference's own artefacts hold for the network-simplex
+path: .sol objectives, published pivot counts, NetworkSimplexTests.cs flow vectors, analyzer
+thresholds, LEMON's known-answer cases, and cost agreement with the vendored LEMON build (oracle/_ref)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import lemon_case_problem
+from mincostflow_b200 import instances
+from mincostflow_b200.instances import Problem
+from oracle import oracle
+
+
+def _cfg(flags=0, **kw):
+    c = oracle.default_config()
+    c.flags = flags
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def test_sol_objectives_all_fixtures(golden, load_fixture):
+    """PerformanceComparisonReport.cs:253-268: cost == .sol objective for every fixture with a .sol (default Solve())."""
+    checked = 0
+    for name, e in golden["fixtures"].items():
+        if not e.get("stored") or "objective" not in e:
+            continue
+        p = load_fixture(name)
+        r, flow, pi, _, _ = oracle.solve(p)                       # default = auto-configuration on
+        assert r.status == oracle.OPTIMAL, name
+        assert r.total_cost == e["objective"], (name, r.total_cost, e["objective"])
+        bad, dual = oracle.validate(p, flow, pi, r.total_cost)
+        assert bad == 0, (name, bad)
+        checked += 1
+    assert checked >= 35
+
+
+@pytest.mark.parametrize("rule", [oracle.FIRST_ELIGIBLE, oracle.BEST_ELIGIBLE, oracle.BLOCK_SEARCH])
+def test_small_fixtures_all_rules(golden, load_fixture, rule):
+    for name, e in golden["fixtures"].items():
+        if not e.get("stored") or "objective" not in e or e["m"] > 10000:
+            continue
+        for opt in (False, True):
+            r, flow, pi, _, _ = oracle.solve(load_fixture(name), pivot_rule=rule, optimized_pivot=opt)
+            assert r.status == oracle.OPTIMAL and r.total_cost == e["objective"], (name, rule, opt)
+
+
+def test_published_pivot_counts(golden, load_fixture):
+    """docs/performance-optimization-final-results.md:50-53 - iterations and block-size trajectory."""
+    p = load_fixture("circulation_1000_0_05")
+    for g in golden["pivot_counts_circulation_1000_0_05"]:
+        r, *_ = oracle.solve(p, config=_cfg(g["flags"], min_block_size=g["min_block_size"], max_block_size=g["max_block_size"]))
+        assert r.status == oracle.OPTIMAL and r.total_cost == golden["fixtures"]["circulation_1000_0_05"]["objective"]
+        assert r.iterations == g["iterations"], (g, r.iterations)
+        assert [r.initial_block_size, r.final_block_size] == g["block"], (g, r.initial_block_size, r.final_block_size)
+
+
+def test_known_answer_flows(golden):
+    """NetworkSimplexTests.cs:28-249."""
+    for k in golden["known_answers"]:
+        p = Problem(k["n"], len(k["src"]), np.asarray(k["src"], np.int32), np.asarray(k["tgt"], np.int32),
+                    np.asarray(k["low"], np.int64), np.asarray(k["up"], np.int64), np.asarray(k["cost"], np.int64),
+                    np.asarray(k["sup"], np.int64), k["name"])
+        r, flow, pi, _, _ = oracle.solve(p)
+        assert r.status == k["status"] and r.total_cost == k["total_cost"], k["name"]
+        assert flow.tolist() == k["flows"], (k["name"], flow.tolist())
+        assert oracle.validate(p, flow, pi, r.total_cost)[0] == 0
+
+
+def test_netgen_generator_reproduces_reference_fixtures(golden):
+    """Resources/netgen/netgen_8_{08,10,13,14}a.min regenerate byte for byte from their header parameters."""
+    for k, prob_no in ((8, 1), (10, 2), (13, 3), (14, 4)):
+        name = f"netgen_8_{k:02d}a"
+        p = instances.netgen8(k)
+        parms = instances.netgen_params(1 << k)
+        found = None
+        for no in range(1, 60):                                   # the banner carries the problem number
+            text = instances.netgen_dimacs_text(no, 13502460, parms, p)
+            if hashlib.sha256(text.encode()).hexdigest() == golden["netgen_sha256"][name]:
+                found = no
+                break
+        assert found is not None, name
+
+
+def test_netgen_objectives(golden):
+    for k in (8, 10, 13, 14):
+        name = f"netgen_8_{k:02d}a"
+        r, flow, pi, _, _ = oracle.solve(instances.netgen8(k))
+        assert r.status == oracle.OPTIMAL and r.total_cost == golden["fixtures"][name]["objective"], name
+
+
+def test_analyzer_thresholds(load_fixture):
+    """ProblemAnalysisTests.cs: dense => SmallBlocksForDense with Min/Max block 10/50 (:202-204); DegreeCV > 0.5 =>
+    adaptive (:250-251); circulation detection (:155); sparse small => reduced-cost caching (OptimizationSelector.cs:47-50)."""
+    p = load_fixture("circulation_1000_0_05")
+    ch = oracle.analyze(p)
+    assert ch.detected_type == 1 and ch.is_dense == 1                  # Circulation; density 0.05 > 0.01
+    cfg = oracle.select_config(ch)
+    assert cfg.flags & oracle.FLAG_SMALL_BLOCKS and cfg.min_block_size == 10 and cfg.max_block_size == 50
+    # hub graph: one node adjacent to all others => DegreeCV > 0.5 => adaptive with the aggressive factors
+    n = 60
+    src = np.zeros(n - 1, np.int32); tgt = np.arange(1, n, dtype=np.int32)
+    hub = Problem(n, n - 1, src, tgt, np.zeros(n - 1, np.int64), np.full(n - 1, 5, np.int64), np.ones(n - 1, np.int64),
+                  np.zeros(n, np.int64), "hub")
+    ch = oracle.analyze(hub)
+    assert ch.degree_cv > 0.5
+    cfg = oracle.select_config(ch)
+    assert cfg.flags & oracle.FLAG_ADAPTIVE and cfg.block_size_growth_factor == 1.3 and cfg.consecutive_hits_before_adapt == 2
+    # NETGEN-8 sits on the DegreeCV 0.3 threshold: the mode flips with size
+    cv = {k: oracle.analyze(instances.netgen8(k)).degree_cv for k in (8, 10, 13)}
+    assert cv[8] > 0.3 and cv[10] > 0.3 and cv[13] < 0.3, cv
+    # config 1 stand-in (10 000 / 30 000): sparse and m < 50 000 => cached Block Search
+    p1 = instances.netgen(13502460, instances.netgen_params(10000, m=30000, sources=100, sinks=100, supply=100000))
+    cfg = oracle.select_config(oracle.analyze(p1))
+    assert cfg.flags & oracle.FLAG_CACHING
+
+
+def test_manual_config_disables_auto(load_fixture):
+    """ProblemAnalysisTests.cs:309-326 / NetworkSimplex.cs:557-561."""
+    p = load_fixture("circulation_100_0_10")
+    r_auto, *_ = oracle.solve(p)
+    r_man, *_ = oracle.solve(p, config=_cfg(0))
+    assert r_man.config_used.flags == 0 and r_auto.config_used.flags != 0
+    assert r_auto.total_cost == r_man.total_cost
+
+
+def test_lemon_known_answers(golden):
+    """min_cost_flow_test.cc:330-422 against the restatement.  All balanced OPTIMAL / INFEASIBLE cases must agree with
+    LEMON's expectations.  The C# port deviates from LEMON on the others, and the restatement keeps those quirks
+    (SURVEY.md A.5): feasibility is only checked on the root->u arcs after `_allArcNum` is clobbered
+    (NetworkSimplex.cs:689, :1272-1283), so unbalanced GEQ/LEQ instances are misreported, and the unbounded test
+    (`!change && delta == 0`, NetworkSimplex.cs:321) never fires on these networks.  For those the test only records
+    that the restatement terminates; the GPU engine is compared with the restatement on the same cases in
+    tests/test_gpu_parity.py."""
+    balanced = 0
+    for case in golden["lemon_cases"]:
+        p, stype, status, total = lemon_case_problem(golden, case)
+        for rule in (oracle.FIRST_ELIGIBLE, oracle.BEST_ELIGIBLE, oracle.BLOCK_SEARCH):
+            r, flow, pi, _, _ = oracle.solve(p, pivot_rule=rule, supply_type=stype)
+            assert r.status in (1, 2, 3)
+            if int(p.supply.sum()) != 0 or status == 3:
+                continue
+            balanced += 1
+            assert r.status == status, (case[0], rule, r.status)
+            if status == 1:
+                assert r.total_cost == total, (case[0], rule, r.total_cost)
+                assert oracle.validate(p, flow, pi, r.total_cost, supply_type=stype)[0] == 0, case[0]
+    assert balanced == 30
+
+
+@pytest.mark.skipif(not oracle.lemon_available(), reason="oracle/_ref not built")
+def test_cost_agreement_with_vendored_lemon(golden, load_fixture):
+    """oracle/_ref = LEMON 1.3.1 NetworkSimplex compiled from /root/reference/lemon-1.3.1 (cost/status oracle)."""
+    for name in ("netgen_8_08a", "netgen_8_10a", "grid_5x5", "transport_40x30", "circulation_100_0_10", "assignment_50x50"):
+        p = load_fixture(name)
+        l = oracle.lemon_solve(p)
+        r, *_ = oracle.solve(p)
+        assert l["status"] == r.status == 1 and l["cost"] == r.total_cost == golden["fixtures"][name]["objective"], name
+    for case in golden["lemon_cases"]:
+        p, stype, status, total = lemon_case_problem(golden, case)
+        l = oracle.lemon_solve(p, supply_type=stype)
+        assert l["status"] == status, (case[0], l["status"])
+        if status == 1:
+            assert l["cost"] == total, case[0]
