@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json's metric on its own config: one network-simplex solve of NETGEN-8 2^20 nodes / 2^23 arcs
+(Block Search, auto-configuration off = the canonical comparator of SURVEY.md A.3) per step, per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload netgen20|netgen18|netgen16|batch18]
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract:
+  value         pivots/s, whole job, device-timed: CUDA events around the persistent pivot kernel on the stream it is launched
+                on, inputs resident in HBM (max over ranks of the summed kernel time)
+  e2e           the same metric through the reference-facing API (NetworkSimplex.Solve() over the C ABI of libmcfgpu.so) with
+                HOST buffers: host pre-pass, H2D of the instance, kernel, D2H of flows + potentials are inside the timed region
+  roofline      the stand-alone Best Eligible pricing sweep (the HBM-bound kernel of the path), timed live with CUDA events
+  cpu_baseline  the CPU oracle (C restatement of the reference's NetworkSimplex.cs) on a bounded sample of the same workload
+  pivot_kernel  in-kernel phase split of the persistent kernel (pricing / cycle / update) and its own pricing GB/s
+N > 1 (torchrun, one rank per GPU): every rank solves its own NETGEN instance of the same size (seed + rank) - a single
+solve is sequential across pivots and does not shard - results are gathered on rank 0 over NCCL.
+`--impl reference` times the CPU oracle (oracle/, the restated reference) on the box's host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 13502460
+WORKLOADS = {
+    # name: (log2 n, instances per rank per step, CPU sample pivots)
+    "netgen20": (20, 1, 600_000),
+    "netgen18": (18, 1, 300_000),
+    "netgen16": (16, 1, 0),
+    "batch18": (18, 8, 300_000),          # BASELINE.json config 5: 64 instances of 2^18 nodes = 8 per GPU at 8 GPUs
+}
+
+
+def workload_name(w):
+    k, per, _ = WORKLOADS[w]
+    return (f"NETGEN-8 2^{k} nodes / 2^{k + 3} arcs, seed {SEED}+i, Block Search, auto-configuration off"
+            + (f", {per} instances per GPU per step" if per > 1 else ""))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_instances(workload, rank):
+    from mincostflow_b200 import instances
+    k, per, _ = WORKLOADS[workload]
+    return [instances.netgen8(k, seed=SEED + rank * per + i) for i in range(per)]
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_cpu():
+    path = os.path.join(ROOT, "tests", "golden", "large.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+
+def run_reference(args):
+    """The reference's own CPU path (restated: oracle/ns_oracle.c) on a bounded sample: the first P pivots of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    k, per, sample = WORKLOADS[args.workload]
+    p = make_instances(args.workload, 0)[0]
+    cfg = oracle.default_config()
+    times, pivots = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=sample)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt); pivots.append(r.iterations)
+    total_t = sum(times); total_p = sum(pivots)
+    value = total_p / total_t
+    sample_txt = (f"first {sample} pivots" if sample else "the full solve") + f" of one {workload_name(args.workload)} instance per step"
+    out = {"impl": "reference", "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": {"workload": workload_name(args.workload), "sample": sample_txt},
+           "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt},
+           "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+
+def run_ours(args):
+    import torch
+    import mincostflow_b200 as mcf
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if mcf.device_count() <= 0:
+        raise SystemExit("bench.py: no sm_100 GPU visible - the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    k, per, sample = WORKLOADS[args.workload]
+    probs = make_instances(args.workload, rank)
+    solvers = []
+    for p in probs:
+        ns = mcf.NetworkSimplex.from_problem(p, device=local_rank)
+        ns.SetPivotRule(mcf.PivotRule.BlockSearch)
+        ns.SetOptimizationConfig(mcf.OptimizationConfig())
+        solvers.append(ns)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        """One pass of the hot path over this rank's batch; returns (pivots, kernel_us, launches, h2d, d2h, result tensor)."""
+        piv = kus = h2d = d2h = 0
+        launches = 0
+        res = []
+        for ns in solvers:
+            ns._dirty = True                                   # host buffers are marshalled and uploaded again every step
+            st = ns.Solve()
+            M = ns.GetMetrics()
+            assert st == mcf.SolverStatus.Optimal, st
+            piv += M.iterations; kus += M.kernel_time_us; h2d += M.h2d_bytes; d2h += M.d2h_bytes; launches += 1
+            res.append((int(st), M.iterations, ns.GetTotalCost(), int(ns.flows().sum()), int(ns.potentials().sum())))
+        return piv, kus, launches, h2d, d2h, res
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    tot_piv = tot_kus = tot_h2d = tot_d2h = tot_launch = 0
+    last = None
+    for _ in range(args.steps):
+        piv, kus, launches, h2d, d2h, last = step()
+        tot_piv += piv; tot_kus += kus; tot_h2d += h2d; tot_d2h += d2h; tot_launch += launches
+        if dist is not None:                                   # NCCL gather of the result records on rank 0
+            rec = torch.tensor(last, dtype=torch.int64, device=dev)
+            gathered = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
+            dist.gather(rec, gathered, dst=0)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # max over ranks of the timed region, sums of the work
+    stats = torch.tensor([wall, tot_kus, float(tot_piv), float(tot_h2d), float(tot_d2h), float(tot_launch)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, kus_max = mx[0].item(), mx[1].item()
+        piv_all, h2d_all, d2h_all, launch_all = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
+    else:
+        kus_max = tot_kus; piv_all, h2d_all, d2h_all, launch_all = tot_piv, tot_h2d, tot_d2h, tot_launch
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    M = solvers[0].GetMetrics()
+    peak, peak_src = measured_peak()
+    # roofline kernel: stand-alone Best Eligible pricing sweep over all S arcs of the same instance, L2 flushed between launches
+    ms, arc, S = solvers[0].pricing_probe(reps=12, flush_l2=True)
+    sweep_ms = float(np.mean(ms[2:]))
+    achieved = 16.0 * S / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload)
+    value = piv_all / (kus_max * 1e-6)
+    e2e = piv_all / wall
+    out = {
+        "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "instances_per_gpu_per_step": per, "pivots_per_step_rank0": tot_piv // args.steps,
+                   "l2": "inputs larger than L2 (arc arrays 16 B x %d arcs; every step re-uploads them)" % S,
+                   "grid_ctas": M.grid_ctas, "pricing_kind": M.pricing_kind, "block_size": M.initial_block_size},
+        "solve_ms": {"kernel": kus_max / 1e3 / args.steps / per, "end_to_end": 1e3 * wall / args.steps / per},
+        "e2e": {"value": e2e, "unit": "pivots/s", "h2d_bytes_per_step": int(h2d_all / args.steps), "d2h_bytes_per_step": int(d2h_all / args.steps)},
+        "gpu_launches": int(launch_all),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "ns_price_sweep_kernel (Best Eligible full scan, 16 B/arc x S arcs per launch)",
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "ms_per_launch": sweep_ms, "arcs_per_launch": int(S)},
+        "pivot_kernel": {"us_per_pivot": M.kernel_time_us / max(M.iterations, 1),
+                         "pricing_us_per_pivot": M.pivot_search_time_us / max(M.iterations, 1),
+                         "cycle_us_per_pivot": M.cycle_time_us / max(M.iterations, 1),
+                         "update_us_per_pivot": M.tree_update_time_us / max(M.iterations, 1),
+                         "arcs_priced_per_pivot": M.arcs_priced / max(M.iterations, 1),
+                         "pricing_GBps_in_kernel": M.pricing_bytes / max(M.pivot_search_time_us, 1e-9) / 1e3},
+    }
+    # CPU baseline (oracle port) on a bounded sample + the GPU on the very same sample
+    if not args.no_cpu and world == 1:
+        from oracle import oracle
+        t0 = time.perf_counter()
+        r, *_ = oracle.solve(probs[0], pivot_rule=oracle.BLOCK_SEARCH, config=oracle.default_config(), max_pivots=sample)
+        cpu_s = time.perf_counter() - t0
+        sample_txt = (f"first {sample} pivots" if sample else "the full solve") + " of the same instance"
+        out["cpu_baseline"] = {"value": r.iterations / cpu_s, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt,
+                               "seconds": cpu_s, "loop_seconds": r.loop_seconds}
+        if sample:
+            ns = solvers[0]
+            ns.set_engine_options(stop_after_pivots=sample)
+            ns._dirty = True
+            t0 = time.perf_counter(); ns.Solve(); gw = time.perf_counter() - t0
+            Ms = ns.GetMetrics()
+            ns.set_engine_options(stop_after_pivots=0)
+            out["cpu_baseline"]["gpu_same_sample"] = {"pivots": Ms.iterations, "kernel_pivots_per_s": Ms.iterations / (Ms.kernel_time_us * 1e-6),
+                                                      "e2e_pivots_per_s": Ms.iterations / gw}
+        rec = recorded_cpu()
+        name = probs[0].name
+        if rec and name in rec:
+            out["cpu_baseline"]["recorded_full_solve"] = {
+                "oracle_port_s": rec[name].get("oracle_loop_seconds"), "lemon_1_3_1_s": rec[name].get("lemon_seconds"),
+                "pivots": rec[name].get("pivots"), "where": "build container (8 vCPU Xeon, shared), tests/golden/large.json"}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="netgen20", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
