@@ -85,7 +85,7 @@ typedef struct mcf_options {
     int32_t device;                 /* CUDA device ordinal */
     int32_t max_ctas;               /* 0 = one CTA per SM (cooperative-launch limit) */
     int32_t lookahead_blocks;       /* blocks priced in the first pricing round of a search; 0 = default (2) */
-    int32_t reserved0;
+    int32_t engine;                 /* 0 = automatic; 1 = flat engine (mcf_kernels.cu); 2 = team engine (mcf_team.cu, Block Search) */
     int64_t stop_after_pivots;      /* >0: stop after this many pivots with Status = NotSolved (bounded samples) */
     double barrier_timeout_s;       /* 0 = default 10 s */
     mcf_optimization_config config; /* SetOptimizationConfig, NetworkSimplex.cs:557-561 (used when auto_configuration == 0) */
@@ -114,6 +114,11 @@ typedef struct mcf_metrics {
     int32_t config_flags;               /* OptimizationFlags actually used (after auto-configuration) */
     int32_t grid_ctas;
     double degree_cv;                   /* ProblemCharacteristics.DegreeCV when auto-configured, else 0 */
+    int32_t engine;                     /* 1 = flat engine, 2 = team engine */
+    int32_t reserved0;
+    int64_t stem_exchanges;             /* team engine: pivots whose re-hung stem was longer than one node */
+    double hop_wait_done_us;            /* team engine: pricing CTA waiting for the owners' updates to become visible */
+    double stem_exchange_us;
 } mcf_metrics;
 
 typedef struct mcf_handle mcf_handle;

@@ -24,6 +24,9 @@ extern "C" int mcfk_pivot_smem_bytes();
 extern "C" int mcfk_max_grid(int device, int* sm_count);
 extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
+extern "C" size_t mcfk_team_smem_bytes(int slice);
+extern "C" int mcfk_team_max_slice(int device);
+extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream);
 
 namespace {
 
@@ -76,6 +79,12 @@ struct mcf_handle {
     DevBuf<mcf::CycEnt> d_list;
     DevBuf<mcf::Ctl> d_ctl;
     DevBuf<unsigned char> d_flush;
+    // team engine (mcf_team.cu)
+    DevBuf<mcf::NodeRec> d_node;
+    DevBuf<int4> d_mail;                                              // enter | cyc | stemhdr | stemseg
+    DevBuf<unsigned> d_done;
+    DevBuf<long long> d_piout;
+    std::vector<mcf::NodeRec> h_node;
     // host staging for the initial basis
     std::vector<int> h_src, h_tgt, h_cost, h_state, h_in, h_sz, h_parent, h_pd;
     std::vector<long long> h_flow, h_upper, h_pi;
@@ -201,6 +210,7 @@ int bind_device(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release();
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->device_bound = dev;
     }
@@ -291,6 +301,150 @@ int choose_grid(mcf_handle* h, int* sms_out)
     return g;
 }
 
+
+// Team engine (mcf_team.cu): CTA 0 prices, CTAs 1..team-1 own node slices that stay in shared memory.
+// Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine), < 0 on error.
+int choose_team(mcf_handle* h, int* slice_out)
+{
+    int sms = 0;
+    const int maxg = mcfk_max_grid(h->opt.device, &sms);
+    if (maxg <= 1) return 0;
+    const int max_slice = mcfk_team_max_slice(h->opt.device);
+    if (max_slice <= 0) return 0;
+    int limit = sms < maxg ? sms : maxg;
+    if (limit > mcf::kTeamMax) limit = mcf::kTeamMax;
+    if (h->opt.max_ctas > 1 && h->opt.max_ctas < limit) limit = h->opt.max_ctas;
+    const long long nodes = (long long)h->n + 1;
+    long long owners = (nodes + 2047) / 2048;                 // >= 2048 nodes per owner: fewer CTAs make every hop cheaper
+    if (h->opt.max_ctas > 1) owners = limit - 1;
+    if (owners < 1) owners = 1;
+    if (owners > limit - 1) owners = limit - 1;
+    long long slice = (nodes + owners - 1) / owners;
+    slice = (slice + 7) & ~7LL;
+    if (slice > max_slice) {
+        owners = limit - 1;
+        slice = ((nodes + owners - 1) / owners + 7) & ~7LL;
+        if (slice > max_slice) return 0;
+    }
+    *slice_out = (int)slice;
+    return (int)owners + 1;
+}
+
+int upload_team(mcf_handle* h, int team, int slice, mcf::TeamParams* P)
+{
+    const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
+    CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
+    CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
+    CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
+    CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)team * 32));
+    const size_t w_enter = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords, w_seg = (size_t)2 * (n + 1);
+    const size_t seg_off = (w_enter + 2 * w_cyc + 7) & ~(size_t)7;
+    CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
+    h->h_node.resize(n + 1);
+    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].pad = 0; }
+    cudaStream_t st = h->stream;
+    int64_t bytes = 0;
+    auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };
+    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)S * 4));
+    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
+    CUDA_TRY(h, up(h->d_flow.p, h->h_flow.data(), (size_t)A * 8)); CUDA_TRY(h, up(h->d_upper.p, h->h_upper.data(), (size_t)A * 8));
+    CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4));
+    CUDA_TRY(h, up(h->d_node.p, h->h_node.data(), (size_t)(n + 1) * sizeof(mcf::NodeRec)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(mcf::Ctl), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)team * 32 * sizeof(unsigned), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_mail.p, 0, (seg_off + w_seg + 8) * sizeof(int4), st));
+    h->metrics.h2d_bytes = bytes;
+    std::memset(P, 0, sizeof(*P));
+    P->n = n; P->m = m; P->S = S; P->A = A;
+    P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
+    P->node = h->d_node.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
+    P->enter = h->d_mail.p; P->cyc = h->d_mail.p + w_enter; P->stemhdr = h->d_mail.p + w_enter + w_cyc; P->stemseg = h->d_mail.p + seg_off;
+    P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->slice = slice;
+    return MCF_OK;
+}
+
+
+int solve_team(mcf_handle* h, int team, int slice, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
+               clk::time_point t_total, int32_t* status_out)
+{
+    const int n = h->n, m = h->m, S = m + n;
+    auto done = [&](int st) { h->status = st; h->solved_once = true; if (status_out) *status_out = st; h->metrics.total_solve_time_us = us_since(t_total); return MCF_OK; };
+    h->metrics.grid_ctas = team;
+    const auto t_h2d = clk::now();
+    mcf::TeamParams P;
+    int rc = upload_team(h, team, slice, &P);
+    if (rc != MCF_OK) return rc;
+    if (has_lower) {
+        CUDA_TRY(h, h->d_lower.ensure(m));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_lower.p, h->orig_lower.data(), (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+        h->metrics.h2d_bytes += (int64_t)m * 8;
+        P.orig_lower = h->d_lower.p;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->metrics.h2d_time_us = us_since(t_h2d);
+
+    P.block_size = block > 0 ? block : 1; P.dyn_min_block = dyn_min; P.max_block_size = cfg.max_block_size;
+    P.adaptive = (cfg.flags & MCF_FLAG_ADAPTIVE_BLOCK_SIZE) ? 1 : 0; P.consecutive = cfg.consecutive_hits_before_adapt;
+    P.low_thr = cfg.low_hit_rate_threshold; P.high_thr = cfg.high_hit_rate_threshold;
+    P.shrink = cfg.block_size_shrink_factor; P.grow = cfg.block_size_growth_factor;
+    P.max_iterations = std::max<int64_t>(1000000LL, (int64_t)n * m);                                  // NS.cs:280
+    P.stop_after = h->opt.stop_after_pivots;
+    const double tmo = h->opt.barrier_timeout_s > 0 ? h->opt.barrier_timeout_s : 10.0;
+    P.timeout_cycles = (unsigned long long)(tmo * 1.9e9);
+
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(h, cudaEventCreate(&ev0)); CUDA_TRY(h, cudaEventCreate(&ev1));
+    CUDA_TRY(h, cudaEventRecord(ev0, h->stream));
+    const int lrc = mcfk_launch_team(&P, h->stream);
+    if (lrc != 0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(h, MCF_ERR_CUDA, "cooperative launch of the team kernel failed: %s", cudaGetErrorString((cudaError_t)lrc)); }
+    CUDA_TRY(h, cudaEventRecord(ev1, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(h, MCF_ERR_CUDA, "team kernel failed: %s", cudaGetErrorString(se)); }
+    float kms = 0; cudaEventElapsedTime(&kms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    h->metrics.kernel_time_us = kms * 1000.0;
+
+    const auto t_d2h = clk::now();
+    mcf::Ctl ctl;
+    CUDA_TRY(h, cudaMemcpyAsync(&ctl, h->d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+    h->flow.resize(m); h->pi.resize(n);
+    CUDA_TRY(h, cudaMemcpyAsync(h->flow.data(), h->d_flow.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->pi.data(), h->d_piout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->metrics.d2h_time_us = us_since(t_d2h);
+    h->metrics.d2h_bytes = (int64_t)m * 8 + (int64_t)n * 8 + (int64_t)sizeof(ctl);
+
+    mcf_metrics& M = h->metrics;
+    M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
+    M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
+    M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
+    M.pivot_search_time_us = ctl.ns_price / 1000.0; M.cycle_time_us = ctl.ns_cycle / 1000.0;
+    M.tree_update_time_us = (ctl.ns_update + ctl.ns_wait_done + ctl.ns_stem) / 1000.0;
+    M.hop_wait_done_us = ctl.ns_wait_done / 1000.0; M.stem_exchange_us = ctl.ns_stem / 1000.0; M.stem_exchanges = ctl.stem_exchanges;
+    M.degenerate_pivots = ctl.degenerate; M.cycle_nodes = ctl.cycle_nodes; M.moved_nodes = ctl.moved_nodes;
+    M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
+    M.arcs_priced = ctl.arcs_checked; M.pricing_bytes = 16 * M.arcs_priced; M.engine = 2;
+    h->total_cost = ctl.total_cost;
+
+    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots", (long long)ctl.iterations); }
+    if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
+        done(MCF_NOT_SOLVED);
+        return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kStemCap);
+    }
+    int st;
+    switch (ctl.status) {
+        case mcf::ST_OPTIMAL: st = ctl.infeasible ? MCF_INFEASIBLE : MCF_OPTIMAL; break;             // NS.cs:360-393
+        case mcf::ST_INFEASIBLE: st = MCF_INFEASIBLE; break;
+        case mcf::ST_UNBOUNDED: st = MCF_UNBOUNDED; break;
+        default: st = MCF_NOT_SOLVED; break;
+    }
+    if (st == MCF_OPTIMAL && has_lower) {                                                            // NS.cs:375-388 (supplies)
+        for (int i = 0; i < m; ++i) if (h->orig_lower[i] != 0) { h->supply[h->source[i]] += h->orig_lower[i]; h->supply[h->target[i]] -= h->orig_lower[i]; }
+    }
+    (void)S;
+    return done(st);
+}
+
 }  // namespace
 
 // ================================================================================================= C ABI
@@ -312,7 +466,7 @@ void mcf_default_options(mcf_options* o)
     if (!o) return;
     std::memset(o, 0, sizeof(*o));
     o->supply_type = MCF_GEQ; o->pivot_rule = MCF_BLOCK_SEARCH; o->auto_configuration = 1; o->optimized_pivot = 0;
-    o->device = 0; o->max_ctas = 0; o->lookahead_blocks = 0; o->stop_after_pivots = 0; o->barrier_timeout_s = 0;
+    o->device = 0; o->max_ctas = 0; o->lookahead_blocks = 0; o->engine = 0; o->stop_after_pivots = 0; o->barrier_timeout_s = 0;
     default_config(&o->config);
 }
 
@@ -344,6 +498,7 @@ void mcf_destroy(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release();
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -436,6 +591,13 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     build_initial_basis(h, art_cost);
     h->metrics.host_prepass_time_us = us_since(t_pre);
 
+    // engine: the team engine (node slices resident in shared memory) runs plain Block Search; everything else, and
+    // instances whose slices do not fit, run on the flat engine (mcf_kernels.cu).  opt.engine: 0 auto, 1 flat, 2 team.
+    int team = 0, slice = 0;
+    if (kind == mcf::PK_BLOCK && h->opt.engine != 1) team = choose_team(h, &slice);
+    if (h->opt.engine == 2 && team <= 0) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but not applicable (pricing kind %d, n = %d)", kind, n);
+    if (team > 0) return solve_team(h, team, slice, block, dyn_min, cfg, has_lower, t_total, status_out);
+
     int sms = 0;
     const int grid = choose_grid(h, &sms);
     if (grid <= 0) return grid;
@@ -497,7 +659,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     if (kind == mcf::PK_BEST) M.arcs_priced = ctl.pricing_rounds * (int64_t)S;
     else if (kind == mcf::PK_FIRST) M.arcs_priced = 0;       // not tracked for First Eligible
     else M.arcs_priced = ctl.arcs_checked;
-    M.pricing_bytes = 16 * M.arcs_priced;
+    M.pricing_bytes = 16 * M.arcs_priced; M.engine = 1;
     h->total_cost = ctl.total_cost;
 
     if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "grid barrier timed out after %lld pivots", (long long)ctl.iterations); }

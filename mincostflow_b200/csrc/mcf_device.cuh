@@ -59,6 +59,8 @@ struct Ctl {                            // control block in global memory (zeroe
     long long max_cycle, max_stem;
     long long pricing_rounds;           // grid-wide pricing rounds (each = one barrier)
     unsigned long long ns_price, ns_cycle, ns_update, ns_total;   // %globaltimer deltas seen by CTA 0
+    unsigned long long ns_wait_done, ns_wait_cyc, ns_stem;        // team engine: hop waits of the pricing CTA
+    long long stem_exchanges;                                     // team engine: pivots that needed the stem exchange
 };
 
 struct Params {
@@ -85,6 +87,43 @@ struct Params {
     long long max_iterations;           // NS.cs:280
     long long stop_after;               // >0: stop after this many pivots (bounded samples / tests)
     unsigned long long barrier_timeout_cycles;
+};
+
+// ------------------------------------------------------------------------------------------------ team engine
+// (mcf_team.cu) node slices resident in shared memory, CTAs exchange 16-byte self-validating words through L2.
+
+struct __align__(16) NodeRec {          // global mirror of a node, read by the pricing gathers (one 128-bit load)
+    long long pi;                       // potential (NS.cs:48)
+    int in;                             // current depth-first index of the node in the basis tree
+    int pad;
+};
+
+constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
+constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
+constexpr int kNodeSmemBytes = 22;      // per resident node: in, sz, pd (int), cycle-list slot (u16), pi (int64)
+
+struct TeamParams {
+    int n, m, S, A;
+    const int* src; const int* tgt; const int* cost;     // [S]
+    int* state;                                          // [A]
+    long long* flow;                                     // [A]
+    const long long* upper;                              // [A]
+    const long long* orig_lower;                         // [m] or nullptr
+    NodeRec* node;                                       // [n+1] (root = n)
+    const int* sz0; const int* pd0;                      // [n+1] initial basis
+    long long* pi_out;                                   // [n]
+    int4* enter;                                         // [2][kMailWords]           pricer -> all
+    int4* cyc;                                           // [2][team][kMailWords]     owner -> all
+    int4* stemhdr;                                       // [2][team][kMailWords]     owner -> all (stem exchange)
+    int4* stemseg;                                       // [2][n+1]                  stem entries, owner o at its slice offset
+    unsigned int* done;                                  // [team][32]                owner -> pricer
+    Ctl* ctl;
+    int team;                                            // CTAs: CTA 0 prices, CTAs 1..team-1 own node slices
+    int slice;                                           // nodes per owner
+    int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
+    double low_thr, high_thr, shrink, grow;
+    long long max_iterations, stop_after;
+    unsigned long long timeout_cycles;
 };
 
 }  // namespace mcf

@@ -78,7 +78,7 @@ class _CConfig(C.Structure):
 class _COptions(C.Structure):
     _fields_ = [("supply_type", C.c_int32), ("pivot_rule", C.c_int32), ("auto_configuration", C.c_int32),
                 ("optimized_pivot", C.c_int32), ("device", C.c_int32), ("max_ctas", C.c_int32),
-                ("lookahead_blocks", C.c_int32), ("reserved0", C.c_int32), ("stop_after_pivots", C.c_int64),
+                ("lookahead_blocks", C.c_int32), ("engine", C.c_int32), ("stop_after_pivots", C.c_int64),
                 ("barrier_timeout_s", C.c_double), ("config", _CConfig)]
 
 
@@ -92,7 +92,9 @@ class SolverMetrics(C.Structure):      # OptimizationTypes.cs:43-69 + engine cou
                 ("d2h_bytes", C.c_int64), ("arcs_priced", C.c_int64), ("pricing_bytes", C.c_int64),
                 ("degenerate_pivots", C.c_int64), ("cycle_nodes", C.c_int64), ("moved_nodes", C.c_int64),
                 ("max_cycle", C.c_int64), ("max_stem", C.c_int64), ("pricing_rounds", C.c_int64),
-                ("config_flags", C.c_int32), ("grid_ctas", C.c_int32), ("degree_cv", C.c_double)]
+                ("config_flags", C.c_int32), ("grid_ctas", C.c_int32), ("degree_cv", C.c_double),
+                ("engine", C.c_int32), ("reserved0", C.c_int32), ("stem_exchanges", C.c_int64),
+                ("hop_wait_done_us", C.c_double), ("stem_exchange_us", C.c_double)]
 
     # reference property names
     Iterations = property(lambda s: s.iterations)
@@ -351,7 +353,8 @@ class NetworkSimplex:
         self._dirty = True
         return self
 
-    def set_engine_options(self, max_ctas=None, lookahead_blocks=None, stop_after_pivots=None, barrier_timeout_s=None, device=None):
+    def set_engine_options(self, max_ctas=None, lookahead_blocks=None, stop_after_pivots=None, barrier_timeout_s=None, device=None, engine=None):
+        if engine is not None: self._opt.engine = {"auto": 0, "flat": 1, "team": 2}.get(engine, engine)
         if max_ctas is not None: self._opt.max_ctas = int(max_ctas)
         if lookahead_blocks is not None: self._opt.lookahead_blocks = int(lookahead_blocks)
         if stop_after_pivots is not None: self._opt.stop_after_pivots = int(stop_after_pivots)

@@ -7,11 +7,11 @@ import mincostflow_b200 as mcf
 from mincostflow_b200 import instances
 from oracle import oracle
 
-def run(p, rule, cfg=None, auto=False, oracle_too=True, max_ctas=None, stop=None, lookahead=None):
+def run(p, rule, cfg=None, auto=False, oracle_too=True, max_ctas=None, stop=None, lookahead=None, engine=None):
     ns = mcf.NetworkSimplex.from_problem(p)
     ns.SetPivotRule(rule)
     if not auto: ns.SetOptimizationConfig(cfg or mcf.OptimizationConfig())
-    ns.set_engine_options(max_ctas=max_ctas, stop_after_pivots=stop, lookahead_blocks=lookahead)
+    ns.set_engine_options(max_ctas=max_ctas, stop_after_pivots=stop, lookahead_blocks=lookahead, engine=engine, barrier_timeout_s=3.0)
     t = time.time()
     try:
         st = ns.Solve()
@@ -22,7 +22,8 @@ def run(p, rule, cfg=None, auto=False, oracle_too=True, max_ctas=None, stop=None
     out = dict(name=p.name, rule=int(rule), status=int(st), pivots=M.iterations, wall_s=round(wall, 4), kernel_ms=round(M.kernel_time_us / 1e3, 3),
                us_per_pivot=round(M.kernel_time_us / max(M.iterations, 1), 3), price_us=round(M.pivot_search_time_us / max(M.iterations, 1), 3),
                cycle_us=round(M.cycle_time_us / max(M.iterations, 1), 3), update_us=round(M.tree_update_time_us / max(M.iterations, 1), 3),
-               grid=M.grid_ctas, rounds=M.pricing_rounds, max_cycle=M.max_cycle, max_stem=M.max_stem, kind=M.pricing_kind, flags=M.config_flags)
+               grid=M.grid_ctas, engine=M.engine, wait_done_us=round(M.hop_wait_done_us / max(M.iterations, 1), 3), stem_x=M.stem_exchanges,
+               stem_us=round(M.stem_exchange_us / max(M.iterations, 1), 3), rounds=M.pricing_rounds, max_cycle=M.max_cycle, max_stem=M.max_stem, kind=M.pricing_kind, flags=M.config_flags)
     if oracle_too:
         oc = None
         if not auto:
@@ -55,6 +56,14 @@ if __name__ == "__main__":
         p = instances.netgen8(16); run(p, 2)
         for g in (8, 32, 74, 148):
             run(p, 2, max_ctas=g, oracle_too=False)
+    elif what == "team":
+        for k in (8, 10, 13, 14, 16):
+            p = instances.netgen8(k)
+            run(p, 2)
+            if k <= 13: run(p, 2, auto=True)
+        p = instances.grid_time_expanded(64, 64); run(p, 2)
+        p = instances.netgen8(18); run(p, 2, oracle_too=False)
+        p = instances.netgen8(20); run(p, 2, oracle_too=False, stop=300000)
     elif what == "big":
         p = instances.netgen8(18); run(p, 2, oracle_too=False)
         p = instances.netgen8(20); run(p, 2, oracle_too=False, stop=200000)
