@@ -119,6 +119,8 @@ typedef struct mcf_metrics {
     int64_t stem_exchanges;             /* team engine: pivots whose re-hung stem was longer than one node */
     double hop_wait_done_us;            /* team engine: pricing CTA waiting for the owners' updates to become visible */
     double stem_exchange_us;
+    double ns_per_clock;                /* team engine: measured SM clock period */
+    double phase_us[16];                /* team engine: sub-phase times (0-7 pricing CTA, 8-15 first owner CTA), see DESIGN.md */
 } mcf_metrics;
 
 typedef struct mcf_handle mcf_handle;

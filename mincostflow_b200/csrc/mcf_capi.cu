@@ -337,7 +337,7 @@ int upload_team(mcf_handle* h, int team, int slice, mcf::TeamParams* P)
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
     CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
     CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)team * 32));
-    const size_t w_enter = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords, w_seg = (size_t)2 * (n + 1);
+    const size_t w_enter = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords, w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
     const size_t seg_off = (w_enter + 2 * w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
@@ -418,9 +418,13 @@ int solve_team(mcf_handle* h, int team, int slice, int block, int dyn_min, const
     M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
     M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
-    M.pivot_search_time_us = ctl.ns_price / 1000.0; M.cycle_time_us = ctl.ns_cycle / 1000.0;
-    M.tree_update_time_us = (ctl.ns_update + ctl.ns_wait_done + ctl.ns_stem) / 1000.0;
-    M.hop_wait_done_us = ctl.ns_wait_done / 1000.0; M.stem_exchange_us = ctl.ns_stem / 1000.0; M.stem_exchanges = ctl.stem_exchanges;
+    // phase accumulators are SM clock ticks (reading %globaltimer costs microseconds); scale by the kernel's own ns / tick
+    const double ns_per_clk = ctl.clk_total > 0 ? (double)ctl.ns_total / (double)ctl.clk_total : 0.0;
+    M.pivot_search_time_us = ctl.ns_price * ns_per_clk / 1000.0; M.cycle_time_us = ctl.ns_cycle * ns_per_clk / 1000.0;
+    M.tree_update_time_us = (ctl.ns_update + ctl.ns_wait_done + ctl.ns_stem) * ns_per_clk / 1000.0;
+    M.hop_wait_done_us = ctl.ns_wait_done * ns_per_clk / 1000.0; M.stem_exchange_us = ctl.ns_stem * ns_per_clk / 1000.0; M.stem_exchanges = ctl.stem_exchanges;
+    M.ns_per_clock = ns_per_clk;
+    for (int i = 0; i < 16; ++i) M.phase_us[i] = ctl.clk[i] * ns_per_clk / 1000.0;
     M.degenerate_pivots = ctl.degenerate; M.cycle_nodes = ctl.cycle_nodes; M.moved_nodes = ctl.moved_nodes;
     M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
     M.arcs_priced = ctl.arcs_checked; M.pricing_bytes = 16 * M.arcs_priced; M.engine = 2;
@@ -429,7 +433,7 @@ int solve_team(mcf_handle* h, int team, int slice, int block, int dyn_min, const
     if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots", (long long)ctl.iterations); }
     if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
         done(MCF_NOT_SOLVED);
-        return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kStemCap);
+        return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kTeamStemCap);
     }
     int st;
     switch (ctl.status) {

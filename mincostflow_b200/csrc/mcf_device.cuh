@@ -61,6 +61,8 @@ struct Ctl {                            // control block in global memory (zeroe
     unsigned long long ns_price, ns_cycle, ns_update, ns_total;   // %globaltimer deltas seen by CTA 0
     unsigned long long ns_wait_done, ns_wait_cyc, ns_stem;        // team engine: hop waits of the pricing CTA
     long long stem_exchanges;                                     // team engine: pivots that needed the stem exchange
+    unsigned long long clk_total;                                 // team engine: clock64 ticks over the loop (phase accumulators are ticks)
+    unsigned long long clk[16];                                   // team engine: sub-phase tick accumulators (0-7 pricing CTA, 8-15 owner CTA 1)
 };
 
 struct Params {
@@ -100,7 +102,8 @@ struct __align__(16) NodeRec {          // global mirror of a node, read by the 
 
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
-constexpr int kNodeSmemBytes = 22;      // per resident node: in, sz, pd (int), cycle-list slot (u16), pi (int64)
+constexpr int kNodeSmemBytes = 28;      // per resident node: in, sz, pd (int), flow and capacity of its pred arc (int64)
+constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages (one entry per thread)
 
 struct TeamParams {
     int n, m, S, A;

@@ -94,7 +94,8 @@ class SolverMetrics(C.Structure):      # OptimizationTypes.cs:43-69 + engine cou
                 ("max_cycle", C.c_int64), ("max_stem", C.c_int64), ("pricing_rounds", C.c_int64),
                 ("config_flags", C.c_int32), ("grid_ctas", C.c_int32), ("degree_cv", C.c_double),
                 ("engine", C.c_int32), ("reserved0", C.c_int32), ("stem_exchanges", C.c_int64),
-                ("hop_wait_done_us", C.c_double), ("stem_exchange_us", C.c_double)]
+                ("hop_wait_done_us", C.c_double), ("stem_exchange_us", C.c_double), ("ns_per_clock", C.c_double),
+                ("phase_us", C.c_double * 16)]
 
     # reference property names
     Iterations = property(lambda s: s.iterations)
@@ -109,7 +110,7 @@ class SolverMetrics(C.Structure):      # OptimizationTypes.cs:43-69 + engine cou
     TreeUpdateTimeMicros = property(lambda s: s.tree_update_time_us)
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "phase_us" else getattr(self, k)) for k, _ in self._fields_}
 
 
 class OptimizationConfig:

@@ -23,7 +23,7 @@ def run(p, rule, cfg=None, auto=False, oracle_too=True, max_ctas=None, stop=None
                us_per_pivot=round(M.kernel_time_us / max(M.iterations, 1), 3), price_us=round(M.pivot_search_time_us / max(M.iterations, 1), 3),
                cycle_us=round(M.cycle_time_us / max(M.iterations, 1), 3), update_us=round(M.tree_update_time_us / max(M.iterations, 1), 3),
                grid=M.grid_ctas, engine=M.engine, wait_done_us=round(M.hop_wait_done_us / max(M.iterations, 1), 3), stem_x=M.stem_exchanges,
-               stem_us=round(M.stem_exchange_us / max(M.iterations, 1), 3), rounds=M.pricing_rounds, max_cycle=M.max_cycle, max_stem=M.max_stem, kind=M.pricing_kind, flags=M.config_flags)
+               stem_us=round(M.stem_exchange_us / max(M.iterations, 1), 3), nsclk=round(M.ns_per_clock, 4), ph=[round(x / max(M.iterations, 1), 2) for x in M.phase_us], rounds=M.pricing_rounds, max_cycle=M.max_cycle, max_stem=M.max_stem, kind=M.pricing_kind, flags=M.config_flags)
     if oracle_too:
         oc = None
         if not auto:
@@ -64,6 +64,10 @@ if __name__ == "__main__":
         p = instances.grid_time_expanded(64, 64); run(p, 2)
         p = instances.netgen8(18); run(p, 2, oracle_too=False)
         p = instances.netgen8(20); run(p, 2, oracle_too=False, stop=300000)
+    elif what == "quick":
+        p = instances.netgen8(13); run(p, 2)
+        p = instances.netgen8(16); run(p, 2)
+        p = instances.netgen8(20); run(p, 2, oracle_too=False, stop=200000)
     elif what == "big":
         p = instances.netgen8(18); run(p, 2, oracle_too=False)
         p = instances.netgen8(20); run(p, 2, oracle_too=False, stop=200000)
