@@ -84,7 +84,7 @@ typedef struct mcf_options {
                                        the managed rules.  Block Search: not supported yet -> MCF_ERR_INVALID_ARGUMENT */
     int32_t device;                 /* CUDA device ordinal */
     int32_t max_ctas;               /* 0 = one CTA per SM (cooperative-launch limit) */
-    int32_t lookahead_blocks;       /* blocks priced in the first pricing round of a search; 0 = default (2) */
+    int32_t lookahead_blocks;       /* flat engine: blocks priced in the first pricing round (0 = 2); team engine: pricing CTAs (0 = auto) */
     int32_t engine;                 /* 0 = automatic; 1 = flat engine (mcf_kernels.cu); 2 = team engine (mcf_team.cu, Block Search) */
     int64_t stop_after_pivots;      /* >0: stop after this many pivots with Status = NotSolved (bounded samples) */
     double barrier_timeout_s;       /* 0 = default 10 s */
@@ -115,12 +115,14 @@ typedef struct mcf_metrics {
     int32_t grid_ctas;
     double degree_cv;                   /* ProblemCharacteristics.DegreeCV when auto-configured, else 0 */
     int32_t engine;                     /* 1 = flat engine, 2 = team engine */
-    int32_t reserved0;
+    int32_t pricer_ctas;                /* team engine: CTAs that price (the rest of grid_ctas own node slices) */
     int64_t stem_exchanges;             /* team engine: pivots whose re-hung stem was longer than one node */
     double hop_wait_done_us;            /* team engine: pricing CTA waiting for the owners' updates to become visible */
     double stem_exchange_us;
     double ns_per_clock;                /* team engine: measured SM clock period */
     double phase_us[16];                /* team engine: sub-phase times (0-7 pricing CTA, 8-15 first owner CTA), see DESIGN.md */
+    int32_t wide_flows;                 /* team engine: 1 = tree-arc flows resident as int64, 0 = int32 */
+    int32_t reserved1;
 } mcf_metrics;
 
 typedef struct mcf_handle mcf_handle;

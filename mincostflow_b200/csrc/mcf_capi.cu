@@ -24,8 +24,9 @@ extern "C" int mcfk_pivot_smem_bytes();
 extern "C" int mcfk_max_grid(int device, int* sm_count);
 extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
-extern "C" size_t mcfk_team_smem_bytes(int slice);
-extern "C" int mcfk_team_max_slice(int device);
+extern "C" size_t mcfk_team_smem_bytes(int slice, int wide);
+extern "C" int mcfk_team_max_slice(int device, int wide);
+extern "C" int mcfk_team_max_ctas(int device, int slice, int wide);
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream);
 
 namespace {
@@ -302,43 +303,51 @@ int choose_grid(mcf_handle* h, int* sms_out)
 }
 
 
-// Team engine (mcf_team.cu): CTA 0 prices, CTAs 1..team-1 own node slices that stay in shared memory.
-// Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine), < 0 on error.
-int choose_team(mcf_handle* h, int* slice_out)
+// Team engine (mcf_team.cu): the first `pricers` CTAs price, the others own node slices that stay in shared memory.
+// Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine).
+int choose_team(mcf_handle* h, int wide, int* slice_out, int* pricers_out)
 {
-    int sms = 0;
-    const int maxg = mcfk_max_grid(h->opt.device, &sms);
-    if (maxg <= 1) return 0;
-    const int max_slice = mcfk_team_max_slice(h->opt.device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->opt.device) != cudaSuccess) return 0;
+    const int max_slice = mcfk_team_max_slice(h->opt.device, wide);
     if (max_slice <= 0) return 0;
-    int limit = sms < maxg ? sms : maxg;
+    int limit = prop.multiProcessorCount;
     if (limit > mcf::kTeamMax) limit = mcf::kTeamMax;
     if (h->opt.max_ctas > 1 && h->opt.max_ctas < limit) limit = h->opt.max_ctas;
+    if (limit < 2) return 0;
     const long long nodes = (long long)h->n + 1;
-    long long owners = (nodes + 2047) / 2048;                 // >= 2048 nodes per owner: fewer CTAs make every hop cheaper
-    if (h->opt.max_ctas > 1) owners = limit - 1;
-    if (owners < 1) owners = 1;
-    if (owners > limit - 1) owners = limit - 1;
+    const long long S = (long long)h->m + h->n;
+    const long long need = (nodes + max_slice - 1) / max_slice;                 // owners the slices need at least
+    if (need > limit - 1) return 0;
+    // pricers: one SM is gather-bound on a whole block; ~384 arcs of the first block per pricer
+    const long long B = (long long)std::sqrt((double)S);
+    long long pricers = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (B + 383) / 384;
+    if (pricers < 1) pricers = 1;
+    if (pricers > mcf::kMaxPricers) pricers = mcf::kMaxPricers;
+    if (pricers > limit - need) pricers = limit - need;
+    // owners: ~1024 nodes each when SMs are to spare (fewer CTAs make every hop cheaper), never fewer than needed
+    long long owners = (nodes + 1023) / 1024;
+    if (owners < need) owners = need;
+    if (owners > limit - pricers) owners = limit - pricers;
     long long slice = (nodes + owners - 1) / owners;
     slice = (slice + 7) & ~7LL;
-    if (slice > max_slice) {
-        owners = limit - 1;
-        slice = ((nodes + owners - 1) / owners + 7) & ~7LL;
-        if (slice > max_slice) return 0;
-    }
-    *slice_out = (int)slice;
-    return (int)owners + 1;
+    if (slice > max_slice) return 0;
+    const int team = (int)(owners + pricers);
+    if (mcfk_team_max_ctas(h->opt.device, (int)slice, wide) < team) return 0;
+    *slice_out = (int)slice; *pricers_out = (int)pricers;
+    return team;
 }
 
-int upload_team(mcf_handle* h, int team, int slice, mcf::TeamParams* P)
+int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::TeamParams* P)
 {
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
     CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
     CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)team * 32));
-    const size_t w_enter = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords, w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
-    const size_t seg_off = (w_enter + 2 * w_cyc + 7) & ~(size_t)7;
+    const size_t w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords;
+    const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
+    const size_t seg_off = (2 * w_pr + w_late + 2 * w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
     for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].pad = 0; }
@@ -358,21 +367,22 @@ int upload_team(mcf_handle* h, int team, int slice, mcf::TeamParams* P)
     P->n = n; P->m = m; P->S = S; P->A = A;
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
     P->node = h->d_node.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
-    P->enter = h->d_mail.p; P->cyc = h->d_mail.p + w_enter; P->stemhdr = h->d_mail.p + w_enter + w_cyc; P->stemseg = h->d_mail.p + seg_off;
-    P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->slice = slice;
+    P->ent0 = h->d_mail.p; P->prc = h->d_mail.p + w_pr; P->late = h->d_mail.p + 2 * w_pr; P->cyc = h->d_mail.p + 2 * w_pr + w_late;
+    P->stemhdr = P->cyc + w_cyc; P->stemseg = h->d_mail.p + seg_off;
+    P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
     return MCF_OK;
 }
 
 
-int solve_team(mcf_handle* h, int team, int slice, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
-               clk::time_point t_total, int32_t* status_out)
+int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
+               clk::time_point t_total, int32_t* status_out, bool* needs_wide)
 {
     const int n = h->n, m = h->m, S = m + n;
     auto done = [&](int st) { h->status = st; h->solved_once = true; if (status_out) *status_out = st; h->metrics.total_solve_time_us = us_since(t_total); return MCF_OK; };
     h->metrics.grid_ctas = team;
     const auto t_h2d = clk::now();
     mcf::TeamParams P;
-    int rc = upload_team(h, team, slice, &P);
+    int rc = upload_team(h, team, pricers, slice, wide, &P);
     if (rc != MCF_OK) return rc;
     if (has_lower) {
         CUDA_TRY(h, h->d_lower.ensure(m));
@@ -414,10 +424,12 @@ int solve_team(mcf_handle* h, int team, int slice, int block, int dyn_min, const
     h->metrics.d2h_time_us = us_since(t_d2h);
     h->metrics.d2h_bytes = (int64_t)m * 8 + (int64_t)n * 8 + (int64_t)sizeof(ctl);
 
+    if (ctl.needs_wide && !wide) { *needs_wide = true; return MCF_OK; }     // a flow left the int32 range: the caller re-runs wide
     mcf_metrics& M = h->metrics;
     M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
     M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
+    M.pricer_ctas = pricers; M.wide_flows = wide;
     // phase accumulators are SM clock ticks (reading %globaltimer costs microseconds); scale by the kernel's own ns / tick
     const double ns_per_clk = ctl.clk_total > 0 ? (double)ctl.ns_total / (double)ctl.clk_total : 0.0;
     M.pivot_search_time_us = ctl.ns_price * ns_per_clk / 1000.0; M.cycle_time_us = ctl.ns_cycle * ns_per_clk / 1000.0;
@@ -597,10 +609,20 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
 
     // engine: the team engine (node slices resident in shared memory) runs plain Block Search; everything else, and
     // instances whose slices do not fit, run on the flat engine (mcf_kernels.cu).  opt.engine: 0 auto, 1 flat, 2 team.
-    int team = 0, slice = 0;
-    if (kind == mcf::PK_BLOCK && h->opt.engine != 1) team = choose_team(h, &slice);
-    if (h->opt.engine == 2 && team <= 0) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but not applicable (pricing kind %d, n = %d)", kind, n);
-    if (team > 0) return solve_team(h, team, slice, block, dyn_min, cfg, has_lower, t_total, status_out);
+    if (kind == mcf::PK_BLOCK && h->opt.engine != 1) {
+        // narrow mode keeps tree-arc flows / capacities as int32 in shared memory: every capacity is "infinite" (== INF) or < 2^31 - 1
+        int wide = 0;
+        for (int i = 0; i < m && !wide; ++i) if (h->upper[i] != kInf && h->upper[i] >= (int64_t)std::numeric_limits<int32_t>::max()) wide = 1;
+        for (; wide < 2; ++wide) {
+            int slice = 0, pricers = 0;
+            const int team = choose_team(h, wide, &slice, &pricers);
+            if (team <= 0) break;
+            bool needs_wide = false;
+            rc = solve_team(h, team, pricers, slice, wide, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
+            if (rc != MCF_OK || !needs_wide) return rc;
+        }
+        if (h->opt.engine == 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but the instance does not fit (n = %d)", n);
+    } else if (h->opt.engine == 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but not applicable (pricing kind %d)", kind);
 
     int sms = 0;
     const int grid = choose_grid(h, &sms);

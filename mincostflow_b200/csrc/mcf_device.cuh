@@ -26,7 +26,8 @@ constexpr int STATE_UPPER = -1, STATE_TREE = 0, STATE_LOWER = 1;
 // SolverStatus.cs:7-34 (+ engine-internal codes >= 100 that the host turns into error returns)
 enum : int {
     ST_NOT_SOLVED = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_UNBALANCED = 4,
-    ST_ERR_CYCLE_TOO_LONG = 100, ST_ERR_BARRIER_TIMEOUT = 101, ST_ERR_STEM_TOO_LONG = 102, ST_STOPPED_EARLY = 103
+    ST_ERR_CYCLE_TOO_LONG = 100, ST_ERR_BARRIER_TIMEOUT = 101, ST_ERR_STEM_TOO_LONG = 102, ST_STOPPED_EARLY = 103,
+    ST_ERR_NEEDS_WIDE = 104             // team engine, narrow mode: a tree-arc flow left the int32 range (host re-runs wide)
 };
 
 // pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599)
@@ -50,6 +51,8 @@ struct Ctl {                            // control block in global memory (zeroe
     int status;
     int final_block_size;
     int infeasible;                     // CheckFeasibility, NS.cs:1272-1283
+    int needs_wide;                     // team engine, narrow mode: a tree-arc flow left the int32 range
+    int pad0;
     long long iterations;
     long long arcs_checked;             // SolverMetrics.TotalArcsChecked
     long long total_cost;               // GetTotalCost, NS.cs:452-465
@@ -102,8 +105,11 @@ struct __align__(16) NodeRec {          // global mirror of a node, read by the 
 
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
-constexpr int kNodeSmemBytes = 28;      // per resident node: in, sz, pd (int), flow and capacity of its pred arc (int64)
-constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages (one entry per thread)
+constexpr int kMaxPricers = 16;         // pricing CTAs of a team
+constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages
+
+// per resident node: in, sz, pd (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
+constexpr int kNodeSmemNarrow = 20, kNodeSmemWide = 28;
 
 struct TeamParams {
     int n, m, S, A;
@@ -115,14 +121,18 @@ struct TeamParams {
     NodeRec* node;                                       // [n+1] (root = n)
     const int* sz0; const int* pd0;                      // [n+1] initial basis
     long long* pi_out;                                   // [n]
-    int4* enter;                                         // [2][kMailWords]           pricer -> all
+    int4* ent0;                                          // [2][pricers][kMailWords]  pricer -> all: its part of the first block
+    int4* late;                                          // [2][kMailWords]           pricer 0 -> all: result of a multi-block search
+    int4* prc;                                           // [2][pricers][kMailWords]  pricer -> pricers: later rounds of a search
     int4* cyc;                                           // [2][team][kMailWords]     owner -> all
     int4* stemhdr;                                       // [2][team][kMailWords]     owner -> all (stem exchange)
-    int4* stemseg;                                       // [2][n+1]                  stem entries, owner o at its slice offset
-    unsigned int* done;                                  // [team][32]                owner -> pricer
+    int4* stemseg;                                       // [2][n+1][2]               stem entries, owner o at its slice offset
+    unsigned int* done;                                  // [team][32]                owner -> pricers
     Ctl* ctl;
-    int team;                                            // CTAs: CTA 0 prices, CTAs 1..team-1 own node slices
+    int team;                                            // CTAs: [0, pricers) price, [pricers, team) own node slices
+    int pricers;
     int slice;                                           // nodes per owner
+    int wide;                                            // 1: tree-arc flows / capacities resident as int64, 0: int32
     int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
     double low_thr, high_thr, shrink, grow;
     long long max_iterations, stop_after;

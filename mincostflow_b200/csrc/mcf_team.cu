@@ -5,21 +5,23 @@
 // succ_num/last_succ (NS.cs:925-1209).  On B200 a dependent L2 load costs ~150 ns, a DRAM miss ~1 us and a grid-wide
 // barrier ~1.3 us (profiles/r01_micro_latency.txt), so the walks are replaced by flat passes over an interval labelling
 // (in[u] = DFS index, sz[u] = subtree size; see mcf_device.cuh) and the whole basis - labels, pred arcs, and the flow and
-// capacity of every tree arc - is kept in SHARED MEMORY, sliced by node id over the CTAs of the team ("owners").  What
-// has to cross between CTAs per pivot is then tiny, and it crosses as 16-byte words that carry their own sequence number
+// capacity of every tree arc - is kept in SHARED MEMORY, sliced by node id over the "owner" CTAs of the team.  What has
+// to cross between CTAs per pivot is then tiny, and it crosses as 16-byte words that carry their own sequence number
 // (the pivot index) in the same 128-bit store - no fence, no barrier (profiles/r01_micro_hop.txt):
 //
-//   hop 1  ENTER   pricing CTA -> all    entering arc, its endpoints' (pi, in), cost, state, capacity
+//   hop 1  ENTER   every pricer -> all   best candidate of its share of the block (arc, endpoints' (pi, in), cost, state, cap)
 //   hop 2  CYC     every owner -> all    its best leaving-arc candidate per side of the cycle (+ counts)
 //  (hop 2b STEM    every owner -> all    only when the re-hung stem is longer than one node: the stem entries)
-//   hop 3  DONE    every owner -> pricer "my pi / in updates of this pivot are globally visible" (after one fence)
+//   hop 3  DONE    every owner -> pricers "my pi / in updates of this pivot are globally visible" (after one fence)
 //
-// CTA 0 ("pricer") runs BlockSearchPivot.FindEnteringArc (NS.cs:1339-1441) over the arc arrays and the global node
-// mirror {pi, in}; the next block's arc data is staged in its shared memory while the other hops are in flight.  Owners
-// run FindJoinNode + FindLeavingArc as an interval test over their slice, every CTA reduces the candidates redundantly
-// to the same decision (strict '<' on the first walk, '<=' on the second, NS.cs:958-998), owners apply ChangeFlow /
-// UpdateTreeStructure / UpdatePotentials (NS.cs:1012-1209) to the nodes they own in ONE fused pass.  Arc flows of tree
-// arcs live with the node below the arc; flow[] in global memory is written when an arc leaves the tree and at the end.
+// The first CTAs ("pricers") run BlockSearchPivot.FindEnteringArc (NS.cs:1339-1441): the block of B arcs is split evenly
+// over them (one SM alone is gather-throughput bound on a 3072-arc block), each prices its share against the global node
+// mirror {pi, in}, and every CTA picks the same winner from the pricers' records.  The share of the next block is staged
+// in shared memory while the other hops are in flight.  Owners run FindJoinNode + FindLeavingArc as an interval test over
+// their slice, every CTA reduces the candidates redundantly to the same decision (strict '<' on the first walk, '<=' on
+// the second, NS.cs:958-998), owners apply ChangeFlow / UpdateTreeStructure / UpdatePotentials (NS.cs:1012-1209) to the
+// nodes they own in ONE fused pass.  Flows of tree arcs live with the node below the arc; flow[] in global memory is
+// written when an arc leaves the tree and at the end.
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
@@ -30,9 +32,10 @@ namespace mcf {
 
 namespace {
 
-constexpr int kTT = 512;                                // threads per CTA of the team kernel: latency-bound code, 128 registers each
+constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
-constexpr int kPf = 8;                                  // arcs per pricer thread staged ahead (first block up to 4096 arcs)
+constexpr int kPf = 8;                                  // arcs per pricer thread staged ahead
+constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
 __device__ __forceinline__ int4 ld_vol4(const int4* p)
 {
@@ -61,53 +64,33 @@ __device__ __forceinline__ int lo32(long long v) { return (int)(unsigned)(unsign
 __device__ __forceinline__ int hi32(long long v) { return (int)(unsigned)((unsigned long long)v >> 32); }
 __device__ __forceinline__ long long mk64(int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 
-struct Key { long long a; int b; int idx; };
-__device__ __forceinline__ bool key_less(const Key& x, const Key& y) { return x.a < y.a || (x.a == y.a && x.b < y.b); }
-__device__ __forceinline__ Key key_none() { Key k; k.a = LLONG_MAX; k.b = INT_MAX; k.idx = -1; return k; }
-__device__ __forceinline__ Key warp_min(Key k)
+// Lane holding the lexicographic minimum of (a, b) among the lanes with `valid` (-1 when none); three REDUX steps
+// instead of a shuffle tree.  All 32 lanes must call.
+__device__ __forceinline__ int warp_argmin(bool valid, long long a, int b)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Key t;
-        t.a = __shfl_xor_sync(0xffffffffu, k.a, o);
-        t.b = __shfl_xor_sync(0xffffffffu, k.b, o);
-        t.idx = __shfl_xor_sync(0xffffffffu, k.idx, o);
-        if (key_less(t, k)) k = t;
-    }
-    return k;
-}
-
-// pricing candidate ordered by (block, reduced cost, scan offset): the first block in scan order that holds a negative
-// reduced cost wins, inside it the smallest reduced cost, among equals the first in scan order (NS.cs:1349-1395).
-struct PKey { long long rc; int blk; int off; int idx; };
-__device__ __forceinline__ bool pkey_less(const PKey& x, const PKey& y)
-{
-    if (x.blk != y.blk) return x.blk < y.blk;
-    if (x.rc != y.rc) return x.rc < y.rc;
-    return x.off < y.off;
-}
-__device__ __forceinline__ PKey warp_pmin(PKey k)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        PKey t;
-        t.rc = __shfl_xor_sync(0xffffffffu, k.rc, o);
-        t.blk = __shfl_xor_sync(0xffffffffu, k.blk, o);
-        t.off = __shfl_xor_sync(0xffffffffu, k.off, o);
-        t.idx = __shfl_xor_sync(0xffffffffu, k.idx, o);
-        if (pkey_less(t, k)) k = t;
-    }
-    return k;
+    const unsigned m = 0xffffffffu;
+    if (!__any_sync(m, valid)) return -1;
+    const int hi = valid ? hi32(a) : INT_MAX;
+    const int mh = __reduce_min_sync(m, hi);
+    bool c = valid && hi == mh;
+    const unsigned lo = c ? (unsigned)lo32(a) : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(m, lo);
+    c = c && lo == ml;
+    const int bb = c ? b : INT_MAX;
+    const int mb = __reduce_min_sync(m, bb);
+    return __ffs(__ballot_sync(m, c && bb == mb)) - 1;
 }
 
 struct Cand {                       // leaving-arc candidate of one side of the cycle
     long long d;                    // residual in cycle direction
     int in, sz, pd;                 // labels and pred word of the node below the candidate arc
-    int zero;                       // flow on the arc is 0 after the augmentation (-> STATE_LOWER), else STATE_UPPER
+    int zero;                       // bit 0: flow on the arc is 0 after the augmentation (-> STATE_LOWER); bit 1: side 1
 };
 
-struct PWin {                       // payload of a pricing candidate
-    int src, tgt, cost, state, in_s, in_t;
+struct PWin {                       // a pricing candidate
+    long long rc;
+    int off;                        // scan offset from next_arc (< 0: none)
+    int arc, src, tgt, cost, state, in_s, in_t;
     long long pi_s, pi_t, upper;
 };
 
@@ -120,113 +103,169 @@ struct Book {                       // statistics and timers: touched by thread 
 
 struct TeamShared {
     Book bk;
-    Key red[2][kTW];
-    Cand wc[2][kTW];             // per-warp winners' payloads
-    PKey pkey[kTW];
-    PWin pwin[kTW];
-    int4 ent[kMailWords];           // ENTER record of this pivot
-    int nstem, abort, cnt;
+    Cand cl[kCandCap];              // cycle-node candidates of this slice (owner scan)
+    Cand wc[2][kTW];                // per-warp winners (hop 2 gather, owner slow path)
+    PWin pw[kTW];                   // per-warp pricing winners
+    PWin win;                       // entering arc of this pivot
+    int4 rec[kMaxPricers][6];       // pricing records as received
+    int ncand, nstem, abort, cnt;
     int pre[kTeamMax + 1];
 };
+
+// time-out / abort check for spin loops; true = give up
+__device__ __forceinline__ bool spin_check(unsigned& spins, long long& t0, const TeamParams& P)
+{
+    if ((++spins & 255u) != 0) return false;
+    if (t0 == 0) { t0 = clock64(); return false; }
+    if (*(volatile int*)&P.ctl->abort) return true;
+    if ((unsigned long long)(clock64() - t0) > P.timeout_cycles) { *(volatile int*)&P.ctl->abort = 1; return true; }
+    return false;
+}
 
 // poll one self-validating word until its sequence number matches; false = abandoned (abort flag or time-out)
 __device__ __forceinline__ bool poll_word(const int4* p, int seq, int4& out, const TeamParams& P)
 {
-    int4 v = ld_vol4(p);
-    if (v.w == seq) { out = v; return true; }
-    const long long t0 = clock64();
-    unsigned spins = 0;
+    unsigned spins = 0; long long t0 = 0;
     for (;;) {
-        v = ld_vol4(p);
+        const int4 v = ld_vol4(p);
         if (v.w == seq) { out = v; return true; }
-        if ((++spins & 255u) == 0) {
-            if (*(volatile int*)&P.ctl->abort) { out = v; return false; }
-            if ((unsigned long long)(clock64() - t0) > P.timeout_cycles) { *(volatile int*)&P.ctl->abort = 1; out = v; return false; }
-        }
+        if (spin_check(spins, t0, P)) { out = v; return false; }
     }
 }
 
+// poll NW words of one record, all loads in flight together
+template <int NW>
+__device__ __forceinline__ bool poll_rec(const int4* rec, int seq, int4 (&w)[NW], const TeamParams& P)
+{
+    unsigned spins = 0; long long t0 = 0;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = ld_vol4(rec + i);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ok = ok && w[i].w == seq;
+        if (ok) return true;
+        if (spin_check(spins, t0, P)) return false;
+    }
+}
+
+__device__ __forceinline__ void post_pwin(int4* rec, const PWin& w, int round, int seq, int lane)
+{
+    int4 o;
+    if (lane == 0) o = make_int4(w.off >= 0 ? w.arc : -1, w.src, w.tgt, seq);
+    else if (lane == 1) o = make_int4(w.cost, w.state, round, seq);
+    else if (lane == 2) o = make_int4(lo32(w.pi_s), hi32(w.pi_s), w.in_s, seq);
+    else if (lane == 3) o = make_int4(lo32(w.pi_t), hi32(w.pi_t), w.in_t, seq);
+    else if (lane == 4) o = make_int4(lo32(w.upper), hi32(w.upper), w.off, seq);
+    else o = make_int4(lo32(w.rc), hi32(w.rc), 0, seq);
+    st_vol4(rec + lane, o);
+}
+__device__ __forceinline__ PWin unpack_pwin(const int4* r)
+{
+    PWin w;
+    w.arc = r[0].x; w.src = r[0].y; w.tgt = r[0].z; w.cost = r[1].x; w.state = r[1].y;
+    w.pi_s = mk64(r[2].x, r[2].y); w.in_s = r[2].z; w.pi_t = mk64(r[3].x, r[3].y); w.in_t = r[3].z;
+    w.upper = mk64(r[4].x, r[4].y); w.off = r[0].x >= 0 ? r[4].z : -1; w.rc = mk64(r[5].x, r[5].y);
+    return w;
+}
+__device__ __forceinline__ PWin pwin_none()
+{
+    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = 0; w.pi_s = w.pi_t = w.upper = 0;
+    return w;
+}
+__device__ __forceinline__ Cand cand_none() { Cand c; c.d = 0; c.in = c.sz = c.zero = 0; c.pd = -1; return c; }
+
+template <typename F> struct FlowTraits;
+template <> struct FlowTraits<int> {
+    __device__ static __forceinline__ int cap_in(long long up) { return up >= (long long)INT_MAX ? INT_MAX : (int)up; }        // INT_MAX = uncapacitated
+    __device__ static __forceinline__ long long residual(int up, int fl) { return up == INT_MAX ? (LLONG_MAX / 2) - fl : (long long)up - fl; }
+    __device__ static __forceinline__ bool fits(long long v) { return v >= 0 && v < (long long)INT_MAX; }
+    __device__ static __forceinline__ long long cap_out(int up) { return up == INT_MAX ? (LLONG_MAX / 2) : (long long)up; }     // the host admits only INF or < 2^31-1
+};
+template <> struct FlowTraits<long long> {
+    __device__ static __forceinline__ long long cap_in(long long up) { return up; }
+    __device__ static __forceinline__ long long residual(long long up, long long fl) { return up == LLONG_MAX ? (LLONG_MAX / 2) : up - fl; }   // NS.cs:970-971
+    __device__ static __forceinline__ bool fits(long long) { return true; }
+    __device__ static __forceinline__ long long cap_out(long long up) { return up; }
+};
+
 }  // namespace
 
+template <typename F>
 __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 {
+    using FT = FlowTraits<F>;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ TeamShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = P.team, cta = blockIdx.x, nown = G - 1;
+    const int G = P.team, NP = P.pricers, cta = blockIdx.x, nown = G - NP;
     const int n = P.n, S = P.S;
-    const bool pricer = cta == 0;
-    const int own = cta - 1;
+    const bool pricer = cta < NP;
+    const int own = cta - NP;
     const int lo = pricer ? 0 : own * P.slice;
     const int cntn = pricer ? 0 : max(0, min(n + 1, lo + P.slice) - lo);
 
-    // dynamic shared memory.  Everybody: stem staging.  Owners: the resident slice.  Pricer: the staged next block.
+    // dynamic shared memory.  Everybody: stem staging.  Owners: the resident slice.  Pricers: the staged share of the next block.
     long long* const st_fl = reinterpret_cast<long long*>(dyn_smem);            // [kTeamStemCap] flow on stem k's old pred arc (after augmentation)
-    int* const st_in = reinterpret_cast<int*>(st_fl + kTeamStemCap);                // [kTeamStemCap] sorted: stem 0 = u_in (deepest) .. u_out
+    int* const st_in = reinterpret_cast<int*>(st_fl + kTeamStemCap);            // sorted: stem 0 = u_in (deepest) .. u_out
     int* const st_z = st_in + kTeamStemCap;
     int* const st_pd = st_z + kTeamStemCap;
-    int* const tmp_in = st_pd + kTeamStemCap;
+    int* const st_up = st_pd + kTeamStemCap;                                    // capacity of that arc (INT_MAX: infinite, -1: fetch)
+    int* const tmp_in = st_up + kTeamStemCap;
     unsigned char* const body = reinterpret_cast<unsigned char*>(tmp_in + kTeamStemCap);
     // owners
-    long long* const fl_s = reinterpret_cast<long long*>(body);                 // flow on the pred arc of node j
-    long long* const up_s = fl_s + P.slice;                                     // capacity of the pred arc
+    F* const fl_s = reinterpret_cast<F*>(body);                                 // flow on the pred arc of node j
+    F* const up_s = fl_s + P.slice;                                             // capacity of the pred arc
     int* const in_s = reinterpret_cast<int*>(up_s + P.slice);
     int* const sz_s = in_s + P.slice;
     int* const pd_s = sz_s + P.slice;
-    // pricer
+    // pricers
     long long* const pf_up = reinterpret_cast<long long*>(body);                // [kPf * kTT]
     int* const pf_src = reinterpret_cast<int*>(pf_up + kPf * kTT);
     int* const pf_tgt = pf_src + kPf * kTT;
     int* const pf_cost = pf_tgt + kPf * kTT;
     int* const pf_st = pf_cost + kPf * kTT;
 
-    for (int j = tid; j < cntn; j += kTT) {
-        const int u = lo + j;
-        const int pd = P.pd0[u];
-        in_s[j] = P.node[u].in; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
-        fl_s[j] = pd >= 0 ? P.flow[pd >> 1] : 0; up_s[j] = pd >= 0 ? P.upper[pd >> 1] : 0;
-    }
-    if (tid == 0) sh.abort = 0;
-    __syncthreads();
-
-    // pricer state (BlockSearchPivot fields, NS.cs:1294-1302)
-    int next_arc = 0, B = P.block_size;
-    int pf_next = -1, pf_B = 0;                          // what is staged: block [pf_next, pf_next + pf_B) of the cyclic scan
-    int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0;   // state changes decided after the staging loads
-    // replicated state
-    long long iterations = 0;
     int status = ST_NOT_SOLVED;
-    // phase accumulators in SM clock ticks (a %globaltimer read costs microseconds, so it is read twice per solve)
-    if (tid == 0) {
-        Book z = {};
-        sh.bk = z;
-        sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64();
+    {
+        int bad = 0;
+        for (int j = tid; j < cntn; j += kTT) {
+            const int u = lo + j;
+            const int pd = P.pd0[u];
+            in_s[j] = P.node[u].in; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
+            const long long fl = pd >= 0 ? P.flow[pd >> 1] : 0, up = pd >= 0 ? P.upper[pd >> 1] : 0;
+            bad |= !FT::fits(fl);
+            fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
+        }
+        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; }
+        if (__syncthreads_or(bad)) { if (tid == 0) P.ctl->needs_wide = 1; }
     }
-#define PROBE(i) do { if (tid == 0 && ((i) < 8 ? pricer : cta == 1)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
-#define TICK(acc) do { if (pricer && tid == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
+    if (tid == 0) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
+
+    // pricer state (BlockSearchPivot fields, NS.cs:1294-1302); identical in every pricer
+    int next_arc = 0, B = P.block_size;
+    int pf_next = -1, pf_B = 0;                          // what is staged: this pricer's share of block [pf_next, pf_next + pf_B)
+    int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0;   // state changes decided after the staging loads
+    long long iterations = 0;
+#define PROBE(i) do { if (tid == 0 && ((i) < 8 ? cta == 0 : cta == NP)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
+#define TICK(acc) do { if (cta == 0 && tid == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
 
     for (;;) {
         const long long k = iterations + 1;
         const int seq = (int)(unsigned)k;
         const int par = (int)(k & 1);
+        bool have_win = false;                            // sh.win holds the entering arc
+        int search_end = 0;                               // pricers: scan offset just past the winning block
 
-        // ================================================================ pricer: wait DONE(k-1), price, post ENTER(k)
+        // ================================================================ pricers: wait DONE(k-1), price their share, post
         if (pricer) {
             if (k > 1) {
                 if (tid < nown) {
                     const unsigned want = (unsigned)(k - 1);
-                    const unsigned* p = P.done + (size_t)(tid + 1) * 32;
-                    if (ld_vol_u32(p) != want) {
-                        const long long t0 = clock64();
-                        unsigned spins = 0;
-                        while (ld_vol_u32(p) != want) {
-                            if ((++spins & 255u) == 0) {
-                                if (*(volatile int*)&P.ctl->abort) { sh.abort = 1; break; }
-                                if ((unsigned long long)(clock64() - t0) > P.timeout_cycles) { *(volatile int*)&P.ctl->abort = 1; sh.abort = 1; break; }
-                            }
-                        }
-                    }
+                    const unsigned* p = P.done + (size_t)(NP + tid) * 32;
+                    unsigned spins = 0; long long t0 = 0;
+                    while (ld_vol_u32(p) != want) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
                 }
                 __syncthreads();
                 if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
@@ -234,268 +273,351 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             TICK(t_wdone);
             PROBE(0);
 
-            // ---- BlockSearchPivot.FindEnteringArc, NS.cs:1339-1397
-            bool found = false;
-            int arcs_this = 0;
-            long long off0 = 0;
-            bool first_group = true;
-            const bool staged = pf_next == next_arc && pf_B == B;
-            for (;;) {
-                const int nb = first_group ? 1 : 8;
-                long long hi = off0 + (long long)nb * B; if (hi > S) hi = S;
-                PKey best; best.rc = 0; best.blk = INT_MAX; best.off = INT_MAX; best.idx = warp;
-                PWin bw; bw.src = bw.tgt = bw.cost = bw.state = bw.in_s = bw.in_t = 0; bw.pi_s = bw.pi_t = bw.upper = 0;
-                if (first_group && staged) {
-                    // the block was staged in shared memory while the previous pivot's hops were in flight; all gathers of a
-                    // thread are issued before the first use
+            // ---- round 0 of BlockSearchPivot.FindEnteringArc (NS.cs:1339-1397): the first block, split over the pricers
+            const int blk0 = B < S ? B : S;
+            const int seg = (blk0 + NP - 1) / NP;
+            const int s_lo = cta * seg, s_hi = min(blk0, s_lo + seg);
+            PWin best = pwin_none();
+            const bool staged = pf_next == next_arc && pf_B == B && seg <= kPf * kTT;
+            if (staged) {
 #pragma unroll
-                    for (int jb = 0; jb < kPf; jb += 4) {
-                        int4 rs[4], rt[4];
-                        int st[4];
+                for (int jb = 0; jb < kPf; jb += 4) {
+                    if (s_lo + jb * kTT >= s_hi) break;
+                    int4 rs[4], rt[4];
+                    int st[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int off = tid + (jb + j) * kTT;
-                            if (off < hi) {
-                                int idx = next_arc + off; if (idx >= S) idx -= S;
-                                rs[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_src[off]));
-                                rt[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_tgt[off]));
-                                st[j] = idx == patch_arc0 ? patch_st0 : (idx == patch_arc1 ? patch_st1 : pf_st[off]);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int off = tid + (jb + j) * kTT;
-                            if (off < hi) {
-                                const long long ps = mk64(rs[j].x, rs[j].y), pt = mk64(rt[j].x, rt[j].y);
-                                const int c = pf_cost[off];
-                                const long long rc = (long long)st[j] * ((long long)c + ps - pt);
-                                if (rc < best.rc) {
-                                    best.blk = 0; best.rc = rc; best.off = off;
-                                    bw.src = pf_src[off]; bw.tgt = pf_tgt[off]; bw.cost = c; bw.state = st[j]; bw.in_s = rs[j].z; bw.in_t = rt[j].z;
-                                    bw.pi_s = ps; bw.pi_t = pt; bw.upper = pf_up[off];
-                                }
-                            }
+                    for (int j = 0; j < 4; ++j) {
+                        const int q = tid + (jb + j) * kTT, off = s_lo + q;
+                        if (off < s_hi) {
+                            int idx = next_arc + off; if (idx >= S) idx -= S;
+                            rs[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_src[q]));
+                            rt[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_tgt[q]));
+                            st[j] = idx == patch_arc0 ? patch_st0 : (idx == patch_arc1 ? patch_st1 : pf_st[q]);
                         }
                     }
-                } else {
-                    for (long long off = off0 + tid; off < hi; off += kTT) {
-                        int idx = next_arc + (int)off; if (idx >= S) idx -= S;
-                        const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
-                        const int st = __ldcg(P.state + idx);
-                        const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + s));
-                        const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + t));
-                        const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
-                        const long long rc = (long long)st * ((long long)c + ps - pt);
-                        if (rc < 0) {
-                            const int blk = first_group ? 0 : (int)((off - off0) / B);
-                            if (blk < best.blk || (blk == best.blk && rc < best.rc)) {
-                                best.blk = blk; best.rc = rc; best.off = (int)off;
-                                bw.src = s; bw.tgt = t; bw.cost = c; bw.state = st; bw.in_s = rs.z; bw.in_t = rt.z; bw.pi_s = ps; bw.pi_t = pt;
-                                bw.upper = LLONG_MIN;                   // fetched by the winner only
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int q = tid + (jb + j) * kTT, off = s_lo + q;
+                        if (off < s_hi) {
+                            const long long ps = mk64(rs[j].x, rs[j].y), pt = mk64(rt[j].x, rt[j].y);
+                            const int c = pf_cost[q];
+                            const long long rc = (long long)st[j] * ((long long)c + ps - pt);
+                            if (rc < best.rc) {
+                                best.rc = rc; best.off = off; best.src = pf_src[q]; best.tgt = pf_tgt[q]; best.cost = c; best.state = st[j];
+                                best.in_s = rs[j].z; best.in_t = rt[j].z; best.pi_s = ps; best.pi_t = pt; best.upper = pf_up[q];
                             }
                         }
                     }
                 }
-                // warp winner -> shared memory (key + payload), then every thread reduces the 32 warp keys itself
-                {
-                    PKey wk = best; wk.idx = lane;
-                    wk = warp_pmin(wk);
-                    if (wk.idx == lane) {
-                        if (bw.upper == LLONG_MIN && wk.blk != INT_MAX) { int idx = next_arc + wk.off; if (idx >= S) idx -= S; bw.upper = __ldg(P.upper + idx); }
-                        PKey o = wk; o.idx = warp; sh.pkey[warp] = o; sh.pwin[warp] = bw;
+            } else {
+                for (int off = s_lo + tid; off < s_hi; off += kTT) {
+                    int idx = next_arc + off; if (idx >= S) idx -= S;
+                    const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
+                    const int st = __ldcg(P.state + idx);
+                    const long long up = __ldg(P.upper + idx);
+                    const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + s));
+                    const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + t));
+                    const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
+                    const long long rc = (long long)st * ((long long)c + ps - pt);
+                    if (rc < best.rc) {
+                        best.rc = rc; best.off = off; best.src = s; best.tgt = t; best.cost = c; best.state = st;
+                        best.in_s = rs.z; best.in_t = rt.z; best.pi_s = ps; best.pi_t = pt; best.upper = up;
                     }
                 }
-                PROBE(1);
-                __syncthreads();
-                PKey win = sh.pkey[lane & (kTW - 1)];
-                win = warp_pmin(win);
-                if (tid == 0) sh.bk.rounds_total++;
-                if (win.blk != INT_MAX) {
-                    long long end = off0 + (long long)(win.blk + 1) * B; if (end > S) end = S;
-                    arcs_this = (int)end;
-                    const PWin w = sh.pwin[win.idx];
-                    if (tid < 5) {
-                        int widx = next_arc + win.off; if (widx >= S) widx -= S;
-                        int4 o;
-                        if (tid == 0) o = make_int4(widx, w.src, w.tgt, seq);
-                        else if (tid == 1) o = make_int4(w.cost, w.state, 1, seq);
-                        else if (tid == 2) o = make_int4(lo32(w.pi_s), hi32(w.pi_s), w.in_s, seq);
-                        else if (tid == 3) o = make_int4(lo32(w.pi_t), hi32(w.pi_t), w.in_t, seq);
-                        else o = make_int4(lo32(w.upper), hi32(w.upper), 0, seq);
-                        st_vol4(P.enter + (size_t)par * kMailWords + tid, o);
-                        sh.ent[tid] = o;
-                    }
-                    // `_nextArc = e` (NS.cs:1397): the last arc examined, or unchanged after a full sweep that ended inside a block
-                    if (end < S || (long long)S % B == 0) { int e = next_arc + (int)end - 1; if (e >= S) e -= S; next_arc = e; }
-                    found = true;
-                    break;
-                }
-                __syncthreads();                                        // sh.pkey is rewritten by the next group
-                off0 = hi;
-                if (off0 >= S) { arcs_this = S; break; }
-                first_group = false;
             }
-            if (tid == 0) sh.bk.arcs_checked += arcs_this;
-            if (!found) {
-                if (tid < 5) { const int4 o = make_int4(-1, 0, 0, seq); st_vol4(P.enter + (size_t)par * kMailWords + tid, o); sh.ent[tid] = o; }
-            } else if (P.adaptive) {                                    // NS.cs:1399-1438
-                const double hit = arcs_this > 0 ? 1.0 / arcs_this : 0;
-                int cl = sh.bk.cons_low, ch = sh.bk.cons_high;                  // every thread computes the same B; thread 0 stores the counters
-                if (hit < P.low_thr) {
-                    ch = 0; cl++;
-                    if (cl >= P.consecutive) { const int ns = (int)(B * P.shrink); B = P.dyn_min_block > ns ? P.dyn_min_block : ns; cl = 0; }
-                } else if (hit > P.high_thr) {
-                    cl = 0; ch++;
-                    if (ch >= P.consecutive) { const int ns = (int)(B * P.grow); B = P.max_block_size < ns ? P.max_block_size : ns; ch = 0; }
-                } else { cl = 0; ch = 0; }
+            {   // CTA arg-min of (rc, off): warp stage, then warp 0 reduces the kTW warp winners and posts the record
+                const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
+                if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
+                else if (lane == wl) { int idx = next_arc + best.off; if (idx >= S) idx -= S; best.arc = idx; sh.pw[warp] = best; }
                 __syncthreads();
-                if (tid == 0) { sh.bk.cons_low = cl; sh.bk.cons_high = ch; }
+                if (warp == 0) {
+                    const PWin* q = &sh.pw[lane & (kTW - 1)];
+                    const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
+                    PWin mine = pwin_none();
+                    if (ww >= 0) mine = sh.pw[ww];
+                    if (lane < 6) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
+                }
             }
-            __syncthreads();
+            PROBE(1);
+        }
+
+        // ================================================================ all: hop 1, collect the pricers' round-0 records
+        if (tid < NP * 6) {
+            const int p = tid / 6, w = tid - p * 6;
+            int4 v;
+            if (!poll_word(P.ent0 + ((size_t)par * NP + p) * kMailWords + w, seq, v, P)) sh.abort = 1;
+            sh.rec[p][w] = v;
+        }
+        __syncthreads();
+        if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        {
+            int bp = -1; long long brc = 0; int boff = INT_MAX;
+            for (int p = 0; p < NP; ++p) {
+                if (sh.rec[p][0].x < 0) continue;
+                const long long rc = mk64(sh.rec[p][5].x, sh.rec[p][5].y); const int off = sh.rec[p][4].z;
+                if (bp < 0 || rc < brc || (rc == brc && off < boff)) { bp = p; brc = rc; boff = off; }
+            }
+            if (bp >= 0) {
+                if (tid == 0) sh.win = unpack_pwin(sh.rec[bp]);
+                have_win = true;
+                search_end = B < S ? B : S;
+            }
+        }
+        if (!have_win) {
+            if (pricer) {
+                // ---- later rounds: pricer p prices block 1 + (r-1)*NP + p; the lowest block with a negative reduced cost wins
+                const long long nblk = ((long long)S + B - 1) / B;
+                int found_blk = -1;
+                for (int r = 1; found_blk < 0; ++r) {
+                    const long long first_blk = 1 + (long long)(r - 1) * NP;
+                    if (first_blk >= nblk) break;
+                    const long long blk = first_blk + cta;
+                    PWin best = pwin_none();
+                    if (blk < nblk) {
+                        const long long o_lo = blk * B; long long o_hi = o_lo + B; if (o_hi > S) o_hi = S;
+                        for (long long off = o_lo + tid; off < o_hi; off += kTT) {
+                            int idx = next_arc + (int)off; if (idx >= S) idx -= S;
+                            const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
+                            const int st = __ldcg(P.state + idx);
+                            const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + s));
+                            const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + t));
+                            const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
+                            const long long rc = (long long)st * ((long long)c + ps - pt);
+                            if (rc < best.rc) {
+                                best.rc = rc; best.off = (int)off; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
+                                best.in_s = rs.z; best.in_t = rt.z; best.pi_s = ps; best.pi_t = pt;
+                            }
+                        }
+                    }
+                    __syncthreads();                                    // sh.pw / sh.rec of the previous round are consumed
+                    const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
+                    if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
+                    else if (lane == wl) { best.upper = __ldg(P.upper + best.arc); sh.pw[warp] = best; }
+                    __syncthreads();
+                    if (warp == 0) {
+                        const PWin* q = &sh.pw[lane & (kTW - 1)];
+                        const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
+                        PWin mine = pwin_none();
+                        if (ww >= 0) mine = sh.pw[ww];
+                        // words 0, 2..5 first, one fence, then word 1 (which carries the round) as the flag: a round record
+                        // reuses the slot of round r-2 of the same pivot, so the sequence number alone cannot validate it
+                        int4* const dst = P.prc + ((size_t)(r & 1) * NP + cta) * kMailWords;
+                        if (lane < 6 && lane != 1) post_pwin(dst, mine, r, seq, lane);
+                        __syncwarp();
+                        if (lane == 1) { __threadfence(); post_pwin(dst, mine, r, seq, 1); }
+                    }
+                    if (tid < NP * 6) {                                 // round records carry (seq, round)
+                        const int p = tid / 6, w = tid - p * 6;
+                        const int4* src = P.prc + ((size_t)(r & 1) * NP + p) * kMailWords;
+                        unsigned spins = 0; long long t0 = 0;
+                        for (;;) {
+                            const int4 v1 = ld_vol4(src + 1);
+                            if (v1.w == seq && v1.z == r) { sh.rec[p][w] = w == 1 ? v1 : ld_vol4(src + w); break; }
+                            if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                        }
+                    }
+                    __syncthreads();
+                    if (sh.abort) break;
+                    if (tid == 0) sh.bk.rounds_total++;
+                    for (int p = 0; p < NP; ++p) if (sh.rec[p][0].x >= 0) { found_blk = (int)(first_blk + p); if (tid == 0) sh.win = unpack_pwin(sh.rec[p]); break; }
+                }
+                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                if (found_blk >= 0) {
+                    long long e = ((long long)found_blk + 1) * B; if (e > S) e = S;
+                    search_end = (int)e; have_win = true;
+                } else search_end = S;
+                __syncthreads();
+                if (cta == 0 && warp == 0) {
+                    PWin w = have_win ? sh.win : pwin_none();
+                    if (lane < 6) post_pwin(P.late + (size_t)par * kMailWords, w, 0, seq, lane);
+                }
+            } else {
+                if (tid < 6) {
+                    int4 v;
+                    if (!poll_word(P.late + (size_t)par * kMailWords + tid, seq, v, P)) sh.abort = 1;
+                    sh.rec[0][tid] = v;
+                }
+                __syncthreads();
+                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                have_win = sh.rec[0][0].x >= 0;
+                if (have_win && tid == 0) sh.win = unpack_pwin(sh.rec[0]);
+            }
+        }
+        __syncthreads();
+        if (pricer) {
+            // NS.cs:1397-1438: cursor, counters, adaptive block size - every pricer keeps the same copy
+            if (tid == 0) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
+            if (have_win) {
+                const int Bold = B;
+                if (P.adaptive) {
+                    const double hit = search_end > 0 ? 1.0 / search_end : 0;
+                    int cl = sh.bk.cons_low, ch = sh.bk.cons_high;
+                    if (hit < P.low_thr) {
+                        ch = 0; cl++;
+                        if (cl >= P.consecutive) { const int ns = (int)(B * P.shrink); B = P.dyn_min_block > ns ? P.dyn_min_block : ns; cl = 0; }
+                    } else if (hit > P.high_thr) {
+                        cl = 0; ch++;
+                        if (ch >= P.consecutive) { const int ns = (int)(B * P.grow); B = P.max_block_size < ns ? P.max_block_size : ns; ch = 0; }
+                    } else { cl = 0; ch = 0; }
+                    __syncthreads();
+                    if (tid == 0) { sh.bk.cons_low = cl; sh.bk.cons_high = ch; }
+                }
+                // `_nextArc = e` (NS.cs:1397): the last arc examined, or unchanged after a full sweep that ended inside a block
+                if (search_end < S || (long long)S % Bold == 0) { int e = next_arc + search_end - 1; if (e >= S) e -= S; next_arc = e; }
+            }
             TICK(t_price);
             PROBE(2);
-            // ---- stage the next pivot's first block: arc data streams from DRAM while hops 1..3 are in flight
-            if (found && B <= kPf * kTT) {
-                const int lim = B < S ? B : S;
+        }
+        if (!have_win) { status = ST_OPTIMAL; break; }
+        iterations = k;
+        if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
+
+        if (pricer) {
+            // ---- stage this pricer's share of the next pivot's first block: arc data streams from DRAM while hops 2..3 are in flight
+            const int blk0 = B < S ? B : S;
+            const int seg = (blk0 + NP - 1) / NP;
+            if (seg <= kPf * kTT) {
+                const int s_lo = cta * seg, s_hi = min(blk0, s_lo + seg);
 #pragma unroll
                 for (int j = 0; j < kPf; ++j) {
-                    const int off = tid + j * kTT;
-                    if (off < lim) {
+                    const int q = tid + j * kTT, off = s_lo + q;
+                    if (off < s_hi) {
                         int idx = next_arc + off; if (idx >= S) idx -= S;
-                        pf_src[off] = __ldg(P.src + idx); pf_tgt[off] = __ldg(P.tgt + idx); pf_cost[off] = __ldg(P.cost + idx);
-                        pf_st[off] = __ldcg(P.state + idx); pf_up[off] = __ldg(P.upper + idx);
+                        pf_src[q] = __ldg(P.src + idx); pf_tgt[q] = __ldg(P.tgt + idx); pf_cost[q] = __ldg(P.cost + idx);
+                        pf_st[q] = __ldcg(P.state + idx); pf_up[q] = __ldg(P.upper + idx);
                     }
                 }
                 pf_next = next_arc; pf_B = B;
             } else pf_next = -1;
             patch_arc0 = patch_arc1 = -1;
             PROBE(3);
-        } else {
-            PROBE(8);
-            // ============================================================ owners: hop 1, wait ENTER(k)
-            if (tid < 5) {
-                int4 w;
-                if (!poll_word(P.enter + (size_t)par * kMailWords + tid, seq, w, P)) sh.abort = 1;
-                sh.ent[tid] = w;
-            }
-            __syncthreads();
-            if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            PROBE(9);
-        }
+        } else PROBE(9);
 
-        const int in_arc = sh.ent[0].x, a_src = sh.ent[0].y, a_tgt = sh.ent[0].z;
-        const int a_cost = sh.ent[1].x, a_state = sh.ent[1].y;
-        if (in_arc < 0) { status = ST_OPTIMAL; break; }
-        iterations = k;
-        if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
-        const long long pi_src = mk64(sh.ent[2].x, sh.ent[2].y), pi_tgt = mk64(sh.ent[3].x, sh.ent[3].y);
-        const int in_src = sh.ent[2].z, in_tgt = sh.ent[3].z;
-        const long long upper_in = mk64(sh.ent[4].x, sh.ent[4].y);
+        const PWin ent = sh.win;
+        const int in_arc = ent.arc, a_src = ent.src, a_tgt = ent.tgt, a_cost = ent.cost, a_state = ent.state;
+        const long long upper_in = ent.upper;
         const bool lower_state = a_state == STATE_LOWER;
         const int first = lower_state ? a_src : a_tgt;                                  // NS.cs:948-957
-        const int inF = lower_state ? in_src : in_tgt, inS = lower_state ? in_tgt : in_src;
-        const long long piF = lower_state ? pi_src : pi_tgt, piS = lower_state ? pi_tgt : pi_src;
+        const int inF = lower_state ? ent.in_s : ent.in_t, inS = lower_state ? ent.in_t : ent.in_s;
+        const long long piF = lower_state ? ent.pi_s : ent.pi_t, piS = lower_state ? ent.pi_t : ent.pi_s;
 
         // ================================================================ owners: cycle discovery over the slice, post CYC(k)
         if (!pricer) {
-            Key k1 = key_none(), k2 = key_none();
-            Cand b1, b2; b1.d = b2.d = 0; b1.in = b2.in = b1.sz = b2.sz = b1.pd = b2.pd = b1.zero = b2.zero = 0;
-            int c = 0;
-            if (tid == 0) sh.cnt = 0;
+            if (tid == 0) sh.ncand = 0;
+            __syncthreads();
             for (int j = tid; j < cntn; j += kTT) {
                 const int in_u = in_s[j], sz_u = sz_s[j];
                 const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
                 const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
                 if (hasF != hasS) {
-                    c++;
                     const int pd = pd_s[j];
-                    const long long fl = fl_s[j], up = up_s[j];
-                    const long long res = up == LLONG_MAX ? (LLONG_MAX / 2) : up - fl;      // NS.cs:970-971
+                    const F fl = fl_s[j], up = up_s[j];
                     const bool dir_up = pd & 1;
                     // first walk: residual capacity when pred_dir == DOWN, else the flow; second walk mirrored (NS.cs:968, :986)
                     const bool increase = hasF ? !dir_up : dir_up;
-                    Key kk; kk.a = increase ? res : fl; kk.idx = lane;
-                    Cand cd; cd.d = kk.a; cd.in = in_u; cd.sz = sz_u; cd.pd = pd; cd.zero = (!increase) || up == 0;
-                    if (hasF) { kk.b = -in_u; if (key_less(kk, k1)) { k1 = kk; b1 = cd; } }   // strict '<' walking up: deepest minimum
-                    else      { kk.b = in_u;  if (key_less(kk, k2)) { k2 = kk; b2 = cd; } }   // '<=' walking up: shallowest minimum
+                    Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd;
+                    cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
+                    const int slot = atomicAdd(&sh.ncand, 1);
+                    if (slot < kCandCap) sh.cl[slot] = cd;
                 }
             }
-            const int any = __syncthreads_or(c > 0);
+            __syncthreads();
+            const int nc = sh.ncand;
             PROBE(10);
-            if (!any) {
-                if (tid < 5) st_vol4(P.cyc + ((size_t)par * G + cta) * kMailWords + tid, make_int4(0, 0, 0, seq));
+            int4* const rec = P.cyc + ((size_t)par * G + cta) * kMailWords;
+            if (nc == 0) {
+                if (tid < 5) st_vol4(rec + tid, make_int4(0, 0, 0, seq));
             } else {
-                if (__any_sync(0xffffffffu, c > 0)) {
-                    int cw = c;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
-                    if (lane == 0) atomicAdd(&sh.cnt, cw);
-                    k1 = warp_min(k1); k2 = warp_min(k2);
-                    if (k1.idx == lane) sh.wc[0][warp] = b1;
-                    if (k2.idx == lane) sh.wc[1][warp] = b2;
-                } else { k1 = key_none(); k2 = key_none(); }
-                if (lane == 0) { k1.idx = k1.idx >= 0 ? warp : -1; k2.idx = k2.idx >= 0 ? warp : -1; sh.red[0][warp] = k1; sh.red[1][warp] = k2; }
-                __syncthreads();
-                if (warp == 0) {
-                    Key f1 = warp_min(sh.red[0][lane & (kTW - 1)]), f2 = warp_min(sh.red[1][lane & (kTW - 1)]);
-                    if (lane < 5) {
-                        Cand m1, m2; m1.d = m2.d = 0; m1.in = m2.in = m1.sz = m2.sz = m1.pd = m2.pd = m1.zero = m2.zero = 0;
-                        if (f1.idx >= 0) m1 = sh.wc[0][f1.idx];
-                        if (f2.idx >= 0) m2 = sh.wc[1][f2.idx];
-                        int4 w;
-                        if (lane == 0) w = make_int4(sh.cnt, 0, (m1.zero ? 1 : 0) | (m2.zero ? 2 : 0), seq);
-                        else if (lane == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
-                        else if (lane == 2) w = make_int4(m1.sz, m1.pd, f1.idx >= 0 ? 1 : 0, seq);
-                        else if (lane == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
-                        else w = make_int4(m2.sz, m2.pd, f2.idx >= 0 ? 1 : 0, seq);
-                        st_vol4(P.cyc + ((size_t)par * G + cta) * kMailWords + lane, w);
+                Cand m1 = cand_none(), m2 = cand_none();
+                if (nc <= kCandCap) {
+                    if (warp == 0) {
+                        // strict '<' walking up from `first`: deepest minimum; '<=' walking up from `second`: shallowest minimum
+                        Cand c = cand_none();
+                        if (lane < nc) c = sh.cl[lane];
+                        const int w1 = warp_argmin(lane < nc && (c.zero & 2), c.d, -c.in);
+                        const int w2 = warp_argmin(lane < nc && !(c.zero & 2), c.d, c.in);
+                        if (w1 >= 0) m1 = sh.cl[w1];
+                        if (w2 >= 0) m2 = sh.cl[w2];
+                    }
+                } else {
+                    // rare: many cycle nodes in one slice - recompute the candidates and reduce over the whole CTA
+                    Cand b1 = cand_none(), b2 = cand_none();
+                    for (int j = tid; j < cntn; j += kTT) {
+                        const int in_u = in_s[j], sz_u = sz_s[j];
+                        const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
+                        const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
+                        if (hasF != hasS) {
+                            const int pd = pd_s[j];
+                            const F fl = fl_s[j], up = up_s[j];
+                            const bool dir_up = pd & 1;
+                            const bool increase = hasF ? !dir_up : dir_up;
+                            Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd;
+                            cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
+                            if (hasF) { if (b1.pd < 0 || cd.d < b1.d || (cd.d == b1.d && cd.in > b1.in)) b1 = cd; }
+                            else      { if (b2.pd < 0 || cd.d < b2.d || (cd.d == b2.d && cd.in < b2.in)) b2 = cd; }
+                        }
+                    }
+                    const int l1 = warp_argmin(b1.pd >= 0, b1.d, -b1.in), l2 = warp_argmin(b2.pd >= 0, b2.d, b2.in);
+                    if (lane == 0) { sh.wc[0][warp].pd = -1; sh.wc[1][warp].pd = -1; }
+                    __syncwarp();
+                    if (l1 >= 0 && lane == l1) sh.wc[0][warp] = b1;
+                    if (l2 >= 0 && lane == l2) sh.wc[1][warp] = b2;
+                    __syncthreads();
+                    if (warp == 0) {
+                        const Cand c1 = sh.wc[0][lane & (kTW - 1)], c2 = sh.wc[1][lane & (kTW - 1)];
+                        const int w1 = warp_argmin(lane < kTW && c1.pd >= 0, c1.d, -c1.in);
+                        const int w2 = warp_argmin(lane < kTW && c2.pd >= 0, c2.d, c2.in);
+                        if (w1 >= 0) m1 = sh.wc[0][w1];
+                        if (w2 >= 0) m2 = sh.wc[1][w2];
                     }
                 }
+                if (warp == 0 && lane < 5) {
+                    int4 w;
+                    if (lane == 0) w = make_int4(nc, 0, (m1.zero & 1) | ((m2.zero & 1) << 1), seq);
+                    else if (lane == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
+                    else if (lane == 2) w = make_int4(m1.sz, m1.pd, m1.pd >= 0 ? 1 : 0, seq);
+                    else if (lane == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
+                    else w = make_int4(m2.sz, m2.pd, m2.pd >= 0 ? 1 : 0, seq);
+                    st_vol4(rec + lane, w);
+                }
             }
+            PROBE(11);
         }
 
-        PROBE(11);
         // ================================================================ all: hop 2, gather CYC(k) and decide
         {
-            Key k1 = key_none(), k2 = key_none();
-            Cand b1, b2; b1.d = b2.d = 0; b1.in = b2.in = b1.sz = b2.sz = b1.pd = b2.pd = b1.zero = b2.zero = 0;
             if (tid == 0) sh.cnt = 0;
             __syncthreads();
             const int nw = (nown + 31) >> 5;                                            // warps that poll
             if (warp < nw) {
+                Cand b1 = cand_none(), b2 = cand_none();
                 int c = 0;
                 if (tid < nown) {
-                    const int4* rec = P.cyc + ((size_t)par * G + tid + 1) * kMailWords;
-                    int4 w0, w1, w2, w3, w4;
-                    bool ok = poll_word(rec + 0, seq, w0, P);
-                    ok = ok && poll_word(rec + 1, seq, w1, P) && poll_word(rec + 2, seq, w2, P) && poll_word(rec + 3, seq, w3, P) && poll_word(rec + 4, seq, w4, P);
-                    if (!ok) sh.abort = 1;
+                    int4 w[5];
+                    if (!poll_rec<5>(P.cyc + ((size_t)par * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
                     else {
-                        c = w0.x;
-                        if (w2.z) { b1.d = mk64(w1.x, w1.y); b1.in = w1.z; b1.sz = w2.x; b1.pd = w2.y; b1.zero = w0.z & 1; k1.a = b1.d; k1.b = -b1.in; k1.idx = lane; }
-                        if (w4.z) { b2.d = mk64(w3.x, w3.y); b2.in = w3.z; b2.sz = w4.x; b2.pd = w4.y; b2.zero = (w0.z >> 1) & 1; k2.a = b2.d; k2.b = b2.in; k2.idx = lane; }
+                        c = w[0].x;
+                        if (w[2].z) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.zero = w[0].z & 1; }
+                        if (w[4].z) { b2.d = mk64(w[3].x, w[3].y); b2.in = w[3].z; b2.sz = w[4].x; b2.pd = w[4].y; b2.zero = (w[0].z >> 1) & 1; }
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0 && c) atomicAdd(&sh.cnt, c);
-                k1 = warp_min(k1); k2 = warp_min(k2);
-                if (k1.idx == lane) sh.wc[0][warp] = b1;
-                if (k2.idx == lane) sh.wc[1][warp] = b2;
-                if (lane == 0) { k1.idx = k1.idx >= 0 ? warp : -1; k2.idx = k2.idx >= 0 ? warp : -1; sh.red[0][warp] = k1; sh.red[1][warp] = k2; }
+                const int l1 = warp_argmin(b1.pd >= 0, b1.d, -b1.in), l2 = warp_argmin(b2.pd >= 0, b2.d, b2.in);
+                if (lane == 0) { sh.wc[0][warp].pd = -1; sh.wc[1][warp].pd = -1; }
+                __syncwarp();
+                if (l1 >= 0 && lane == l1) sh.wc[0][warp] = b1;
+                if (l2 >= 0 && lane == l2) sh.wc[1][warp] = b2;
             }
             __syncthreads();
             if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            Key f1 = key_none(), f2 = key_none();
+            Cand w1 = cand_none(), w2 = cand_none();
             for (int w = 0; w < nw; ++w) {
-                const Key t1 = sh.red[0][w], t2 = sh.red[1][w];
-                if (t1.idx >= 0 && key_less(t1, f1)) f1 = t1;
-                if (t2.idx >= 0 && key_less(t2, f2)) f2 = t2;
+                const Cand t1 = sh.wc[0][w], t2 = sh.wc[1][w];
+                if (t1.pd >= 0 && (w1.pd < 0 || t1.d < w1.d || (t1.d == w1.d && t1.in > w1.in))) w1 = t1;
+                if (t2.pd >= 0 && (w2.pd < 0 || t2.d < w2.d || (t2.d == w2.d && t2.in < w2.in))) w2 = t2;
             }
-            const bool has1 = f1.idx >= 0, has2 = f2.idx >= 0;
-            Cand w1, w2; w1.d = w2.d = 0; w1.in = w2.in = w1.sz = w2.sz = w1.pd = w2.pd = w1.zero = w2.zero = 0;
-            if (has1) w1 = sh.wc[0][f1.idx];
-            if (has2) w2 = sh.wc[1][f2.idx];
+            const bool has1 = w1.pd >= 0, has2 = w2.pd >= 0;
             const int cnt = sh.cnt;
             TICK(t_cycle);
             PROBE(4); PROBE(12);
@@ -520,11 +642,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // ---- stem = cycle nodes on u_in's side from u_in up to u_out.  One node (74 % of pivots): nothing to exchange.
             if (change && a != in_uin) {
                 // hop 2b: owners publish their stem entries (with the flow AFTER the augmentation), everybody sorts them
-                if (tid == 0) sh.bk.stem_x++;
-                __syncthreads();                                                        // sh.red / sh.wc readers are done
+                if (tid == 0) { sh.bk.stem_x++; sh.nstem = 0; }
+                __syncthreads();
                 if (!pricer) {
-                    if (tid == 0) sh.nstem = 0;
-                    __syncthreads();
                     for (int j = tid; j < cntn; j += kTT) {
                         const int in_u = in_s[j], sz_u = sz_s[j];
                         const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
@@ -536,7 +656,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const int q = atomicAdd(&sh.nstem, 1);
                             int4* e = P.stemseg + ((size_t)par * (n + 1) + lo + q) * 2;
                             st_vol4(e, make_int4(in_u, sz_u, pd, seq));
-                            st_vol4(e + 1, make_int4(lo32(fl), hi32(fl), 0, seq));
+                            const long long upl = FT::cap_out(up_s[j]);                      // capacity travels too when it fits 31 bits (-1: fetch)
+                            st_vol4(e + 1, make_int4(lo32(fl), hi32(fl), upl == LLONG_MAX / 2 ? INT_MAX : (upl < (long long)INT_MAX ? (int)upl : -1), seq));
                         }
                     }
                     __syncthreads();
@@ -545,7 +666,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 int mycnt = 0;
                 if (tid < nown) {
                     int4 w;
-                    if (!poll_word(P.stemhdr + ((size_t)par * G + tid + 1) * kMailWords, seq, w, P)) sh.abort = 1;
+                    if (!poll_word(P.stemhdr + ((size_t)par * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
                     else mycnt = w.x;
                 }
                 if (tid < kTeamMax) sh.pre[tid + 1] = tid < nown ? mycnt : 0;
@@ -567,19 +688,18 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 ns = sh.pre[nown];
                 if (ns > kTeamStemCap || ns < 2) { status = ST_ERR_STEM_TOO_LONG; break; }
                 constexpr int kEnt = kTeamStemCap / kTT;                                // entries per thread
-                int e_in[kEnt], e_z[kEnt], e_pd[kEnt]; long long e_fl[kEnt];
+                int e_in[kEnt], e_z[kEnt], e_pd[kEnt], e_up[kEnt]; long long e_fl[kEnt];
 #pragma unroll
                 for (int i = 0; i < kEnt; ++i) {
                     const int q = tid + i * kTT;
-                    e_in[i] = e_z[i] = e_pd[i] = 0; e_fl[i] = 0;
+                    e_in[i] = e_z[i] = e_pd[i] = e_up[i] = 0; e_fl[i] = 0;
                     if (q < ns) {
                         int l = 0, r = nown;                                            // owner l (0-based) with pre[l] <= q < pre[l+1]
                         while (r - l > 1) { const int mid = (l + r) >> 1; if (sh.pre[mid] <= q) l = mid; else r = mid; }
-                        const int4* e = P.stemseg + ((size_t)par * (n + 1) + (size_t)l * P.slice + (q - sh.pre[l])) * 2;
-                        int4 wa, wb;
-                        if (!poll_word(e, seq, wa, P) || !poll_word(e + 1, seq, wb, P)) sh.abort = 1;
-                        e_in[i] = wa.x; e_z[i] = wa.y; e_pd[i] = wa.z; e_fl[i] = mk64(wb.x, wb.y);
-                        tmp_in[q] = wa.x;
+                        int4 w[2];
+                        if (!poll_rec<2>(P.stemseg + ((size_t)par * (n + 1) + (size_t)l * P.slice + (q - sh.pre[l])) * 2, seq, w, P)) sh.abort = 1;
+                        e_in[i] = w[0].x; e_z[i] = w[0].y; e_pd[i] = w[0].z; e_fl[i] = mk64(w[1].x, w[1].y); e_up[i] = w[1].z;
+                        tmp_in[q] = w[0].x;
                     }
                 }
                 __syncthreads();
@@ -590,7 +710,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     if (q < ns) {                                                       // rank by counting (in[] values are distinct)
                         int rank = 0;
                         for (int r = 0; r < ns; ++r) rank += tmp_in[r] > e_in[i];
-                        st_in[rank] = e_in[i]; st_z[rank] = e_z[i]; st_pd[rank] = e_pd[i]; st_fl[rank] = e_fl[i];
+                        st_in[rank] = e_in[i]; st_z[rank] = e_z[i]; st_pd[rank] = e_pd[i]; st_fl[rank] = e_fl[i]; st_up[rank] = e_up[i];
                     }
                 }
                 __syncthreads();
@@ -601,8 +721,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // ================================================================ updates
             const bool dir_new_up = u_in == a_src;                                      // NS.cs:1143
             if (pricer) {
-                // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scan reads them
-                if (change) { patch_arc0 = in_arc; patch_st0 = STATE_TREE; patch_arc1 = out.pd >> 1; patch_st1 = out.zero ? STATE_LOWER : STATE_UPPER; }
+                // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them; every pricer keeps its own view
+                if (change) { patch_arc0 = in_arc; patch_st0 = STATE_TREE; patch_arc1 = out.pd >> 1; patch_st1 = (out.zero & 1) ? STATE_LOWER : STATE_UPPER; }
                 else { patch_arc0 = in_arc; patch_st0 = -a_state; patch_arc1 = -1; }
                 if (tid == 0) {
                     P.state[patch_arc0] = patch_st0;
@@ -614,6 +734,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int base = b < a ? b + 1 : b - s + 1;                             // new index of u_in: first child of v_in
                 const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
                 const long long sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);   // NS.cs:1187-1188
+                int bad = 0;
                 // one fused pass: ChangeFlow (NS.cs:1012-1040), UpdateTreeStructure (:1042-1183), UpdatePotentials (:1185-1209)
                 for (int j = tid; j < cntn; j += kTT) {
                     const int x = in_s[j], sz_u = sz_s[j];
@@ -621,26 +742,31 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     const bool hasS = (unsigned)(inS - x) < (unsigned)sz_u;
                     if (hasF != hasS) {
                         const int pd = pd_s[j];
-                        long long fl = fl_s[j];
                         if (delta > 0) {                                                // NS.cs:1020-1029
                             const long long dv = (pd & 1) ? val : -val;                 // pred_dir * val
-                            fl = (hasF == src_side1) ? fl - dv : fl + dv;
-                            fl_s[j] = fl;
+                            const long long fl = (hasF == src_side1) ? (long long)fl_s[j] - dv : (long long)fl_s[j] + dv;
+                            bad |= !FT::fits(fl);
+                            fl_s[j] = (F)fl;
                         }
                         if (change) {
                             if (hasF != in_side1) sz_s[j] = sz_u + s;                   // v_in .. join (NS.cs:1174-1177)
                             else if (x < a) sz_s[j] = sz_u - s;                         // v_out .. join (NS.cs:1179-1182)
                             else {                                                      // stem node (NS.cs:1095-1146)
-                                if (x == a) P.flow[pd >> 1] = out.zero ? 0 : up_s[j];   // u_out: its pred arc leaves the tree at a bound
+                                if (x == a) P.flow[pd >> 1] = (out.zero & 1) ? 0 : FT::cap_out(up_s[j]);   // u_out: its pred arc leaves the tree at a bound
                                 int kk = 0;
                                 if (ns > 1) { int l = 0, r = ns - 1; while (l < r) { const int mid = (l + r) >> 1; if (st_in[mid] <= x) r = mid; else l = mid + 1; } kk = l; }
                                 if (kk == 0) {
+                                    const long long nf = (lower_state ? 0 : upper_in) + val;
+                                    bad |= !FT::fits(nf);
                                     pd_s[j] = in_arc * 2 + (dir_new_up ? 1 : 0); sz_s[j] = s;
-                                    fl_s[j] = (lower_state ? 0 : upper_in) + val; up_s[j] = upper_in;
+                                    fl_s[j] = (F)nf; up_s[j] = FT::cap_in(upper_in);
                                 } else {
                                     const int npd = st_pd[kk - 1] ^ 1;
+                                    bad |= !FT::fits(st_fl[kk - 1]);
                                     pd_s[j] = npd; sz_s[j] = s - st_z[kk - 1];
-                                    fl_s[j] = st_fl[kk - 1]; up_s[j] = __ldg(P.upper + (npd >> 1));
+                                    const int upw = st_up[kk - 1];
+                                    fl_s[j] = (F)st_fl[kk - 1];
+                                    up_s[j] = FT::cap_in(upw == INT_MAX ? LLONG_MAX / 2 : (upw >= 0 ? (long long)upw : __ldg(P.upper + (npd >> 1))));
                                 }
                             }
                         }
@@ -670,6 +796,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         }
                     }
                 }
+                if (bad) P.ctl->needs_wide = 1;
                 // hop 3: everything this CTA wrote for pivot k is visible before DONE(k)
                 PROBE(13);
                 __syncthreads();
@@ -682,13 +809,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (P.stop_after > 0 && iterations >= P.stop_after) { status = ST_STOPPED_EARLY; break; }
     }
 #undef TICK
-    if (tid == 0 && (pricer || cta == 1)) for (int i = pricer ? 0 : 8; i < (pricer ? 8 : 16); ++i) P.ctl->clk[i] = sh.bk.pr[i];
+#undef PROBE
+    if (tid == 0 && (cta == 0 || cta == NP)) for (int i = cta == 0 ? 0 : 8; i < (cta == 0 ? 8 : 16); ++i) P.ctl->clk[i] = sh.bk.pr[i];
 
     // =================================================================== epilogue
     const bool clean = status != ST_ERR_BARRIER_TIMEOUT;
     if (clean) {
         // flows of the tree arcs go back to flow[]; then one conventional grid barrier (counter + fences)
-        for (int j = tid; j < cntn; j += kTT) { const int pd = pd_s[j]; if (pd >= 0) P.flow[pd >> 1] = fl_s[j]; }
+        for (int j = tid; j < cntn; j += kTT) { const int pd = pd_s[j]; if (pd >= 0) P.flow[pd >> 1] = (long long)fl_s[j]; }
         __syncthreads();
         if (tid == 0) {
             __threadfence();
@@ -716,7 +844,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&P.ctl->total_cost), (unsigned long long)acc);
     }
-    if (pricer && tid == 0) {
+    if (cta == 0 && tid == 0) {
         Ctl* c = P.ctl;
         const Book& bk = sh.bk;
         c->status = status; c->iterations = iterations; c->arcs_checked = bk.arcs_checked; c->final_block_size = B;
@@ -733,34 +861,46 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 // ------------------------------------------------------------------------------------------------ launchers
 
 namespace {
-constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
+constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 5 * 4);
 constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (8 + 4 * 4);
+inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 
-extern "C" size_t mcfk_team_smem_bytes(int slice)
+extern "C" size_t mcfk_team_smem_bytes(int slice, int wide)
 {
-    const size_t owner = (size_t)slice * mcf::kNodeSmemBytes;
+    const size_t owner = (size_t)slice * (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
     return kStemBytes + (owner > kPricerBytes ? owner : kPricerBytes) + 16;
 }
 
 // largest slice (nodes per owner CTA) that fits the opt-in shared memory of the device next to the kernel's static part
-extern "C" int mcfk_team_max_slice(int device)
+extern "C" int mcfk_team_max_slice(int device, int wide)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, mcf::ns_team_kernel) != cudaSuccess) return -2;
+    if (cudaFuncGetAttributes(&fa, team_fn(wide)) != cudaSuccess) return -2;
     const long long avail = (long long)prop.sharedMemPerBlockOptin - (long long)fa.sharedSizeBytes - (long long)kStemBytes - 64;
-    const long long s = avail / mcf::kNodeSmemBytes;
+    const long long s = avail / (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
     return (int)(s & ~7LL);
+}
+
+extern "C" int mcfk_team_max_ctas(int device, int slice, int wide)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    const size_t smem = mcfk_team_smem_bytes(slice, wide);
+    if (cudaFuncSetAttribute(team_fn(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, team_fn(wide), mcf::kTT, smem) != cudaSuccess) return -3;
+    return per_sm * prop.multiProcessorCount;
 }
 
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream)
 {
-    const size_t smem = mcfk_team_smem_bytes(p->slice);
-    cudaError_t e = cudaFuncSetAttribute(mcf::ns_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = mcfk_team_smem_bytes(p->slice, p->wide);
+    cudaError_t e = cudaFuncSetAttribute(team_fn(p->wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     void* args[] = {(void*)p};
-    e = cudaLaunchCooperativeKernel((const void*)mcf::ns_team_kernel, dim3(p->team), dim3(mcf::kTT), args, smem, stream);
+    e = cudaLaunchCooperativeKernel(team_fn(p->wide), dim3(p->team), dim3(mcf::kTT), args, smem, stream);
     return (int)e;
 }

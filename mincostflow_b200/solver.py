@@ -93,9 +93,9 @@ class SolverMetrics(C.Structure):      # OptimizationTypes.cs:43-69 + engine cou
                 ("degenerate_pivots", C.c_int64), ("cycle_nodes", C.c_int64), ("moved_nodes", C.c_int64),
                 ("max_cycle", C.c_int64), ("max_stem", C.c_int64), ("pricing_rounds", C.c_int64),
                 ("config_flags", C.c_int32), ("grid_ctas", C.c_int32), ("degree_cv", C.c_double),
-                ("engine", C.c_int32), ("reserved0", C.c_int32), ("stem_exchanges", C.c_int64),
+                ("engine", C.c_int32), ("pricer_ctas", C.c_int32), ("stem_exchanges", C.c_int64),
                 ("hop_wait_done_us", C.c_double), ("stem_exchange_us", C.c_double), ("ns_per_clock", C.c_double),
-                ("phase_us", C.c_double * 16)]
+                ("phase_us", C.c_double * 16), ("wide_flows", C.c_int32), ("reserved1", C.c_int32)]
 
     # reference property names
     Iterations = property(lambda s: s.iterations)

@@ -22,7 +22,7 @@ def run(p, rule, cfg=None, auto=False, oracle_too=True, max_ctas=None, stop=None
     out = dict(name=p.name, rule=int(rule), status=int(st), pivots=M.iterations, wall_s=round(wall, 4), kernel_ms=round(M.kernel_time_us / 1e3, 3),
                us_per_pivot=round(M.kernel_time_us / max(M.iterations, 1), 3), price_us=round(M.pivot_search_time_us / max(M.iterations, 1), 3),
                cycle_us=round(M.cycle_time_us / max(M.iterations, 1), 3), update_us=round(M.tree_update_time_us / max(M.iterations, 1), 3),
-               grid=M.grid_ctas, engine=M.engine, wait_done_us=round(M.hop_wait_done_us / max(M.iterations, 1), 3), stem_x=M.stem_exchanges,
+               grid=M.grid_ctas, np=M.pricer_ctas, wide=M.wide_flows, engine=M.engine, wait_done_us=round(M.hop_wait_done_us / max(M.iterations, 1), 3), stem_x=M.stem_exchanges,
                stem_us=round(M.stem_exchange_us / max(M.iterations, 1), 3), nsclk=round(M.ns_per_clock, 4), ph=[round(x / max(M.iterations, 1), 2) for x in M.phase_us], rounds=M.pricing_rounds, max_cycle=M.max_cycle, max_stem=M.max_stem, kind=M.pricing_kind, flags=M.config_flags)
     if oracle_too:
         oc = None
