@@ -350,7 +350,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     const size_t seg_off = (2 * w_pr + w_late + 2 * w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
-    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].pad = 0; }
+    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = u == n ? 0 : 1; }
     cudaStream_t st = h->stream;
     int64_t bytes = 0;
     auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };

@@ -100,7 +100,7 @@ struct Params {
 struct __align__(16) NodeRec {          // global mirror of a node, read by the pricing gathers (one 128-bit load)
     long long pi;                       // potential (NS.cs:48)
     int in;                             // current depth-first index of the node in the basis tree
-    int pad;
+    int dp;                             // current depth of the node (root = 0)
 };
 
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
@@ -108,8 +108,8 @@ constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM 
 constexpr int kMaxPricers = 16;         // pricing CTAs of a team
 constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages
 
-// per resident node: in, sz, pd (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
-constexpr int kNodeSmemNarrow = 20, kNodeSmemWide = 28;
+// per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
+constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32;
 
 struct TeamParams {
     int n, m, S, A;

@@ -85,12 +85,13 @@ struct Cand {                       // leaving-arc candidate of one side of the 
     long long d;                    // residual in cycle direction
     int in, sz, pd;                 // labels and pred word of the node below the candidate arc
     int zero;                       // bit 0: flow on the arc is 0 after the augmentation (-> STATE_LOWER); bit 1: side 1
+    int dp, j;                      // depth of the node; its index in the owner's slice
 };
 
 struct PWin {                       // a pricing candidate
     long long rc;
     int off;                        // scan offset from next_arc (< 0: none)
-    int arc, src, tgt, cost, state, in_s, in_t;
+    int arc, src, tgt, cost, state, in_s, in_t, dp_s, dp_t;
     long long pi_s, pi_t, upper;
 };
 
@@ -107,7 +108,7 @@ struct TeamShared {
     Cand wc[2][kTW];                // per-warp winners (hop 2 gather, owner slow path)
     PWin pw[kTW];                   // per-warp pricing winners
     PWin win;                       // entering arc of this pivot
-    int4 rec[kMaxPricers][6];       // pricing records as received
+    int4 rec[kMaxPricers][7];       // pricing records as received
     int ncand, nstem, abort, cnt;
     int pre[kTeamMax + 1];
 };
@@ -157,7 +158,8 @@ __device__ __forceinline__ void post_pwin(int4* rec, const PWin& w, int round, i
     else if (lane == 2) o = make_int4(lo32(w.pi_s), hi32(w.pi_s), w.in_s, seq);
     else if (lane == 3) o = make_int4(lo32(w.pi_t), hi32(w.pi_t), w.in_t, seq);
     else if (lane == 4) o = make_int4(lo32(w.upper), hi32(w.upper), w.off, seq);
-    else o = make_int4(lo32(w.rc), hi32(w.rc), 0, seq);
+    else if (lane == 5) o = make_int4(lo32(w.rc), hi32(w.rc), 0, seq);
+    else o = make_int4(w.dp_s, w.dp_t, 0, seq);
     st_vol4(rec + lane, o);
 }
 __device__ __forceinline__ PWin unpack_pwin(const int4* r)
@@ -166,14 +168,15 @@ __device__ __forceinline__ PWin unpack_pwin(const int4* r)
     w.arc = r[0].x; w.src = r[0].y; w.tgt = r[0].z; w.cost = r[1].x; w.state = r[1].y;
     w.pi_s = mk64(r[2].x, r[2].y); w.in_s = r[2].z; w.pi_t = mk64(r[3].x, r[3].y); w.in_t = r[3].z;
     w.upper = mk64(r[4].x, r[4].y); w.off = r[0].x >= 0 ? r[4].z : -1; w.rc = mk64(r[5].x, r[5].y);
+    w.dp_s = r[6].x; w.dp_t = r[6].y;
     return w;
 }
 __device__ __forceinline__ PWin pwin_none()
 {
-    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = 0; w.pi_s = w.pi_t = w.upper = 0;
+    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = w.dp_s = w.dp_t = 0; w.pi_s = w.pi_t = w.upper = 0;
     return w;
 }
-__device__ __forceinline__ Cand cand_none() { Cand c; c.d = 0; c.in = c.sz = c.zero = 0; c.pd = -1; return c; }
+__device__ __forceinline__ Cand cand_none() { Cand c; c.d = 0; c.in = c.sz = c.zero = c.dp = c.j = 0; c.pd = -1; return c; }
 
 template <typename F> struct FlowTraits;
 template <> struct FlowTraits<int> {
@@ -212,14 +215,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const st_z = st_in + kTeamStemCap;
     int* const st_pd = st_z + kTeamStemCap;
     int* const st_up = st_pd + kTeamStemCap;                                    // capacity of that arc (INT_MAX: infinite, -1: fetch)
-    int* const tmp_in = st_up + kTeamStemCap;
-    unsigned char* const body = reinterpret_cast<unsigned char*>(tmp_in + kTeamStemCap);
+    unsigned char* const body = reinterpret_cast<unsigned char*>(st_up + kTeamStemCap);
     // owners
     F* const fl_s = reinterpret_cast<F*>(body);                                 // flow on the pred arc of node j
     F* const up_s = fl_s + P.slice;                                             // capacity of the pred arc
     int* const in_s = reinterpret_cast<int*>(up_s + P.slice);
     int* const sz_s = in_s + P.slice;
     int* const pd_s = sz_s + P.slice;
+    int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
     // pricers
     long long* const pf_up = reinterpret_cast<long long*>(body);                // [kPf * kTT]
     int* const pf_src = reinterpret_cast<int*>(pf_up + kPf * kTT);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         for (int j = tid; j < cntn; j += kTT) {
             const int u = lo + j;
             const int pd = P.pd0[u];
-            in_s[j] = P.node[u].in; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
+            in_s[j] = P.node[u].in; dp_s[j] = P.node[u].dp; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
             const long long fl = pd >= 0 ? P.flow[pd >> 1] : 0, up = pd >= 0 ? P.upper[pd >> 1] : 0;
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const long long rc = (long long)st[j] * ((long long)c + ps - pt);
                             if (rc < best.rc) {
                                 best.rc = rc; best.off = off; best.src = pf_src[q]; best.tgt = pf_tgt[q]; best.cost = c; best.state = st[j];
-                                best.in_s = rs[j].z; best.in_t = rt[j].z; best.pi_s = ps; best.pi_t = pt; best.upper = pf_up[q];
+                                best.in_s = rs[j].z; best.in_t = rt[j].z; best.dp_s = rs[j].w; best.dp_t = rt[j].w; best.pi_s = ps; best.pi_t = pt; best.upper = pf_up[q];
                             }
                         }
                     }
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     const long long rc = (long long)st * ((long long)c + ps - pt);
                     if (rc < best.rc) {
                         best.rc = rc; best.off = off; best.src = s; best.tgt = t; best.cost = c; best.state = st;
-                        best.in_s = rs.z; best.in_t = rt.z; best.pi_s = ps; best.pi_t = pt; best.upper = up;
+                        best.in_s = rs.z; best.in_t = rt.z; best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt; best.upper = up;
                     }
                 }
             }
@@ -335,15 +338,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
                     PWin mine = pwin_none();
                     if (ww >= 0) mine = sh.pw[ww];
-                    if (lane < 6) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
+                    if (lane < 7) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
                 }
             }
             PROBE(1);
         }
 
         // ================================================================ all: hop 1, collect the pricers' round-0 records
-        if (tid < NP * 6) {
-            const int p = tid / 6, w = tid - p * 6;
+        if (tid < NP * 7) {
+            const int p = tid / 7, w = tid - p * 7;
             int4 v;
             if (!poll_word(P.ent0 + ((size_t)par * NP + p) * kMailWords + w, seq, v, P)) sh.abort = 1;
             sh.rec[p][w] = v;
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const long long rc = (long long)st * ((long long)c + ps - pt);
                             if (rc < best.rc) {
                                 best.rc = rc; best.off = (int)off; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
-                                best.in_s = rs.z; best.in_t = rt.z; best.pi_s = ps; best.pi_t = pt;
+                                best.in_s = rs.z; best.in_t = rt.z; best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt;
                             }
                         }
                     }
@@ -402,12 +405,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         // words 0, 2..5 first, one fence, then word 1 (which carries the round) as the flag: a round record
                         // reuses the slot of round r-2 of the same pivot, so the sequence number alone cannot validate it
                         int4* const dst = P.prc + ((size_t)(r & 1) * NP + cta) * kMailWords;
-                        if (lane < 6 && lane != 1) post_pwin(dst, mine, r, seq, lane);
+                        if (lane < 7 && lane != 1) post_pwin(dst, mine, r, seq, lane);
                         __syncwarp();
                         if (lane == 1) { __threadfence(); post_pwin(dst, mine, r, seq, 1); }
                     }
-                    if (tid < NP * 6) {                                 // round records carry (seq, round)
-                        const int p = tid / 6, w = tid - p * 6;
+                    if (tid < NP * 7) {                                 // round records carry (seq, round)
+                        const int p = tid / 7, w = tid - p * 7;
                         const int4* src = P.prc + ((size_t)(r & 1) * NP + p) * kMailWords;
                         unsigned spins = 0; long long t0 = 0;
                         for (;;) {
@@ -429,10 +432,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 __syncthreads();
                 if (cta == 0 && warp == 0) {
                     PWin w = have_win ? sh.win : pwin_none();
-                    if (lane < 6) post_pwin(P.late + (size_t)par * kMailWords, w, 0, seq, lane);
+                    if (lane < 7) post_pwin(P.late + (size_t)par * kMailWords, w, 0, seq, lane);
                 }
             } else {
-                if (tid < 6) {
+                if (tid < 7) {
                     int4 v;
                     if (!poll_word(P.late + (size_t)par * kMailWords + tid, seq, v, P)) sh.abort = 1;
                     sh.rec[0][tid] = v;
@@ -500,8 +503,22 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         const int first = lower_state ? a_src : a_tgt;                                  // NS.cs:948-957
         const int inF = lower_state ? ent.in_s : ent.in_t, inS = lower_state ? ent.in_t : ent.in_s;
         const long long piF = lower_state ? ent.pi_s : ent.pi_t, piS = lower_state ? ent.pi_t : ent.pi_s;
+        const int dpF = lower_state ? ent.dp_s : ent.dp_t, dpS = lower_state ? ent.dp_t : ent.dp_s;
 
         // ================================================================ owners: cycle discovery over the slice, post CYC(k)
+        // A node is on the pivot cycle iff exactly one end of the entering arc lies in its subtree (FindJoinNode + both walks
+        // of FindLeavingArc, NS.cs:925-1010, as one interval test per node).
+        auto make_cand = [&](int j, int in_u, int sz_u, bool hasF) -> Cand {
+            const int pd = pd_s[j];
+            const F fl = fl_s[j], up = up_s[j];
+            const bool dir_up = pd & 1;
+            // first walk: residual capacity when pred_dir == DOWN, else the flow; second walk mirrored (NS.cs:968, :986)
+            const bool increase = hasF ? !dir_up : dir_up;
+            Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd; cd.dp = dp_s[j]; cd.j = j;
+            cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
+            return cd;
+        };
+        int nc = 0;
         if (!pricer) {
             if (tid == 0) sh.ncand = 0;
             __syncthreads();
@@ -510,19 +527,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
                 const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
                 if (hasF != hasS) {
-                    const int pd = pd_s[j];
-                    const F fl = fl_s[j], up = up_s[j];
-                    const bool dir_up = pd & 1;
-                    // first walk: residual capacity when pred_dir == DOWN, else the flow; second walk mirrored (NS.cs:968, :986)
-                    const bool increase = hasF ? !dir_up : dir_up;
-                    Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd;
-                    cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
                     const int slot = atomicAdd(&sh.ncand, 1);
-                    if (slot < kCandCap) sh.cl[slot] = cd;
+                    if (slot < kCandCap) sh.cl[slot] = make_cand(j, in_u, sz_u, hasF);
                 }
             }
             __syncthreads();
-            const int nc = sh.ncand;
+            nc = sh.ncand;
             PROBE(10);
             int4* const rec = P.cyc + ((size_t)par * G + cta) * kMailWords;
             if (nc == 0) {
@@ -547,12 +557,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
                         const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
                         if (hasF != hasS) {
-                            const int pd = pd_s[j];
-                            const F fl = fl_s[j], up = up_s[j];
-                            const bool dir_up = pd & 1;
-                            const bool increase = hasF ? !dir_up : dir_up;
-                            Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd;
-                            cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
+                            const Cand cd = make_cand(j, in_u, sz_u, hasF);
                             if (hasF) { if (b1.pd < 0 || cd.d < b1.d || (cd.d == b1.d && cd.in > b1.in)) b1 = cd; }
                             else      { if (b2.pd < 0 || cd.d < b2.d || (cd.d == b2.d && cd.in < b2.in)) b2 = cd; }
                         }
@@ -573,11 +578,11 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
                 if (warp == 0 && lane < 5) {
                     int4 w;
-                    if (lane == 0) w = make_int4(nc, 0, (m1.zero & 1) | ((m2.zero & 1) << 1), seq);
+                    if (lane == 0) w = make_int4(nc, (m1.zero & 1) | ((m2.zero & 1) << 1) | (m1.pd >= 0 ? 4 : 0) | (m2.pd >= 0 ? 8 : 0), 0, seq);
                     else if (lane == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
-                    else if (lane == 2) w = make_int4(m1.sz, m1.pd, m1.pd >= 0 ? 1 : 0, seq);
+                    else if (lane == 2) w = make_int4(m1.sz, m1.pd, m1.dp, seq);
                     else if (lane == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
-                    else w = make_int4(m2.sz, m2.pd, m2.pd >= 0 ? 1 : 0, seq);
+                    else w = make_int4(m2.sz, m2.pd, m2.dp, seq);
                     st_vol4(rec + lane, w);
                 }
             }
@@ -597,8 +602,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     if (!poll_rec<5>(P.cyc + ((size_t)par * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
                     else {
                         c = w[0].x;
-                        if (w[2].z) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.zero = w[0].z & 1; }
-                        if (w[4].z) { b2.d = mk64(w[3].x, w[3].y); b2.in = w[3].z; b2.sz = w[4].x; b2.pd = w[4].y; b2.zero = (w[0].z >> 1) & 1; }
+                        if (w[0].y & 4) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.dp = w[2].z; b1.zero = w[0].y & 1; }
+                        if (w[0].y & 8) { b2.d = mk64(w[3].x, w[3].y); b2.in = w[3].z; b2.sz = w[4].x; b2.pd = w[4].y; b2.dp = w[4].z; b2.zero = (w[0].y >> 1) & 1; }
                     }
                 }
                 c = __reduce_add_sync(0xffffffffu, c);
@@ -634,88 +639,64 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const bool in_side1 = result == 1;
             const int u_in = in_side1 ? first : (lower_state ? a_tgt : a_src);          // NS.cs:999-1008
             const int a = out.in, s = out.sz;                                           // old interval of the re-hung subtree
-            const int in_uin = in_side1 ? inF : inS;
             const int b = in_side1 ? inS : inF;                                         // in[v_in]
+            const int dp_uin = in_side1 ? dpF : dpS, dp_vin = in_side1 ? dpS : dpF;
             const bool src_side1 = lower_state;                                         // is `first` the source of the entering arc?
-            int ns = 1;
+            // stem = cycle nodes on u_in's side from u_in (index 0, deepest) up to u_out (index ns-1); depths give the index
+            const int ns = change ? dp_uin - out.dp + 1 : 1;
+            const bool longstem = ns > kTeamStemCap;
+            int4* const stem_g = P.stemseg + (size_t)par * (n + 1) * 2;                 // entry of stem index k at slot t = ns-1-k
 
-            // ---- stem = cycle nodes on u_in's side from u_in up to u_out.  One node (74 % of pivots): nothing to exchange.
-            if (change && a != in_uin) {
-                // hop 2b: owners publish their stem entries (with the flow AFTER the augmentation), everybody sorts them
-                if (tid == 0) { sh.bk.stem_x++; sh.nstem = 0; }
-                __syncthreads();
+            // new flow on the pred arc of a cycle node (ChangeFlow, NS.cs:1020-1029)
+            auto new_flow = [&](long long fl, int pd, bool hasF) -> long long {
+                if (delta <= 0) return fl;
+                const long long dv = (pd & 1) ? val : -val;                             // pred_dir * val
+                return (hasF == src_side1) ? fl - dv : fl + dv;
+            };
+
+            // ---- hop 2b (26 % of pivots): the stem is longer than one node; its owners publish the entries, index = depth
+            if (ns > 1) {
+                if (tid == 0) sh.bk.stem_x++;
                 if (!pricer) {
-                    for (int j = tid; j < cntn; j += kTT) {
-                        const int in_u = in_s[j], sz_u = sz_s[j];
-                        const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
-                        const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
-                        if (hasF != hasS && hasF == in_side1 && in_u >= a) {
-                            const int pd = pd_s[j];
-                            long long fl = fl_s[j];
-                            if (delta > 0) { const long long dv = (pd & 1) ? val : -val; fl = (hasF == src_side1) ? fl - dv : fl + dv; }
-                            const int q = atomicAdd(&sh.nstem, 1);
-                            int4* e = P.stemseg + ((size_t)par * (n + 1) + lo + q) * 2;
-                            st_vol4(e, make_int4(in_u, sz_u, pd, seq));
-                            const long long upl = FT::cap_out(up_s[j]);                      // capacity travels too when it fits 31 bits (-1: fetch)
-                            st_vol4(e + 1, make_int4(lo32(fl), hi32(fl), upl == LLONG_MAX / 2 ? INT_MAX : (upl < (long long)INT_MAX ? (int)upl : -1), seq));
+                    auto publish = [&](int j, int in_u, int sz_u, int pd, int dp, bool hasF) {
+                        const long long fl = new_flow((long long)fl_s[j], pd, hasF);
+                        const long long upl = FT::cap_out(up_s[j]);                      // capacity travels too when it fits 31 bits (-1: fetch)
+                        int4* e = stem_g + (size_t)(dp - out.dp) * 2;
+                        st_vol4(e, make_int4(in_u, sz_u, pd, seq));
+                        st_vol4(e + 1, make_int4(lo32(fl), hi32(fl), upl == LLONG_MAX / 2 ? INT_MAX : (upl < (long long)INT_MAX ? (int)upl : -1), seq));
+                    };
+                    if (nc <= kCandCap) {
+                        if (tid < nc) {
+                            const Cand c = sh.cl[tid];
+                            const bool hasF = (c.zero & 2) != 0;
+                            if (hasF == in_side1 && c.in >= a) publish(c.j, c.in, c.sz, c.pd, c.dp, hasF);
+                        }
+                    } else {
+                        for (int j = tid; j < cntn; j += kTT) {
+                            const int in_u = in_s[j], sz_u = sz_s[j];
+                            const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
+                            const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
+                            if (hasF != hasS && hasF == in_side1 && in_u >= a) publish(j, in_u, sz_u, pd_s[j], dp_s[j], hasF);
                         }
                     }
-                    __syncthreads();
-                    if (tid == 0) st_vol4(P.stemhdr + ((size_t)par * G + cta) * kMailWords, make_int4(sh.nstem, 0, 0, seq));
                 }
-                int mycnt = 0;
-                if (tid < nown) {
-                    int4 w;
-                    if (!poll_word(P.stemhdr + ((size_t)par * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
-                    else mycnt = w.x;
-                }
-                if (tid < kTeamMax) sh.pre[tid + 1] = tid < nown ? mycnt : 0;
-                if (tid == 0) sh.pre[0] = 0;
-                __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                if (warp == 0) {                                                        // inclusive scan of pre[1..nown]
-                    int carry = 0;
-                    for (int base = 1; base <= nown; base += 32) {
-                        const int i = base + lane;
-                        int v = i <= nown ? sh.pre[i] : 0;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-                        if (i <= nown) sh.pre[i] = v + carry;
-                        carry += __shfl_sync(0xffffffffu, v, 31);
-                    }
-                }
-                __syncthreads();
-                ns = sh.pre[nown];
-                if (ns > kTeamStemCap || ns < 2) { status = ST_ERR_STEM_TOO_LONG; break; }
-                constexpr int kEnt = kTeamStemCap / kTT;                                // entries per thread
-                int e_in[kEnt], e_z[kEnt], e_pd[kEnt], e_up[kEnt]; long long e_fl[kEnt];
-#pragma unroll
-                for (int i = 0; i < kEnt; ++i) {
-                    const int q = tid + i * kTT;
-                    e_in[i] = e_z[i] = e_pd[i] = e_up[i] = 0; e_fl[i] = 0;
-                    if (q < ns) {
-                        int l = 0, r = nown;                                            // owner l (0-based) with pre[l] <= q < pre[l+1]
-                        while (r - l > 1) { const int mid = (l + r) >> 1; if (sh.pre[mid] <= q) l = mid; else r = mid; }
+                if (!longstem && !pricer) {
+                    for (int q = tid; q < ns; q += kTT) {
                         int4 w[2];
-                        if (!poll_rec<2>(P.stemseg + ((size_t)par * (n + 1) + (size_t)l * P.slice + (q - sh.pre[l])) * 2, seq, w, P)) sh.abort = 1;
-                        e_in[i] = w[0].x; e_z[i] = w[0].y; e_pd[i] = w[0].z; e_fl[i] = mk64(w[1].x, w[1].y); e_up[i] = w[1].z;
-                        tmp_in[q] = w[0].x;
+                        if (!poll_rec<2>(stem_g + (size_t)q * 2, seq, w, P)) sh.abort = 1;
+                        const int kx = ns - 1 - q;
+                        st_in[kx] = w[0].x; st_z[kx] = w[0].y; st_pd[kx] = w[0].z; st_fl[kx] = mk64(w[1].x, w[1].y); st_up[kx] = w[1].z;
                     }
+                    __syncthreads();
+                    if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 }
-                __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-#pragma unroll
-                for (int i = 0; i < kEnt; ++i) {
-                    const int q = tid + i * kTT;
-                    if (q < ns) {                                                       // rank by counting (in[] values are distinct)
-                        int rank = 0;
-                        for (int r = 0; r < ns; ++r) rank += tmp_in[r] > e_in[i];
-                        st_in[rank] = e_in[i]; st_z[rank] = e_z[i]; st_pd[rank] = e_pd[i]; st_fl[rank] = e_fl[i]; st_up[rank] = e_up[i];
-                    }
-                }
-                __syncthreads();
                 TICK(t_stem);
             }
+            // stem accessors: shared memory, or (stems longer than the staging area) the published entries themselves
+            auto stem_io = [&](int kx, int& o_in, int& o_z) {
+                if (!longstem) { o_in = st_in[kx]; o_z = st_z[kx]; }
+                else { int4 w; if (!poll_word(stem_g + (size_t)(ns - 1 - kx) * 2, seq, w, P)) sh.abort = 1; o_in = w.x; o_z = w.y; }
+            };
             if (change && tid == 0) { if (ns > sh.bk.max_stem) sh.bk.max_stem = ns; sh.bk.moved_nodes += s; }
 
             // ================================================================ updates
@@ -731,68 +712,81 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             } else {
                 if (!change && delta > 0 && tid == 0 && first >= lo && first < lo + cntn)
                     P.flow[in_arc] = (lower_state ? 0 : upper_in) + val;                // NS.cs:1018: stays a non-tree arc, at the other bound
-                const int base = b < a ? b + 1 : b - s + 1;                             // new index of u_in: first child of v_in
-                const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
-                const long long sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);   // NS.cs:1187-1188
                 int bad = 0;
-                // one fused pass: ChangeFlow (NS.cs:1012-1040), UpdateTreeStructure (:1042-1183), UpdatePotentials (:1185-1209)
-                for (int j = tid; j < cntn; j += kTT) {
-                    const int x = in_s[j], sz_u = sz_s[j];
-                    const bool hasF = (unsigned)(inF - x) < (unsigned)sz_u;
-                    const bool hasS = (unsigned)(inS - x) < (unsigned)sz_u;
-                    if (hasF != hasS) {
-                        const int pd = pd_s[j];
-                        if (delta > 0) {                                                // NS.cs:1020-1029
-                            const long long dv = (pd & 1) ? val : -val;                 // pred_dir * val
-                            const long long fl = (hasF == src_side1) ? (long long)fl_s[j] - dv : (long long)fl_s[j] + dv;
-                            bad |= !FT::fits(fl);
-                            fl_s[j] = (F)fl;
-                        }
-                        if (change) {
-                            if (hasF != in_side1) sz_s[j] = sz_u + s;                   // v_in .. join (NS.cs:1174-1177)
-                            else if (x < a) sz_s[j] = sz_u - s;                         // v_out .. join (NS.cs:1179-1182)
-                            else {                                                      // stem node (NS.cs:1095-1146)
-                                if (x == a) P.flow[pd >> 1] = (out.zero & 1) ? 0 : FT::cap_out(up_s[j]);   // u_out: its pred arc leaves the tree at a bound
-                                int kk = 0;
-                                if (ns > 1) { int l = 0, r = ns - 1; while (l < r) { const int mid = (l + r) >> 1; if (st_in[mid] <= x) r = mid; else l = mid + 1; } kk = l; }
-                                if (kk == 0) {
-                                    const long long nf = (lower_state ? 0 : upper_in) + val;
-                                    bad |= !FT::fits(nf);
-                                    pd_s[j] = in_arc * 2 + (dir_new_up ? 1 : 0); sz_s[j] = s;
-                                    fl_s[j] = (F)nf; up_s[j] = FT::cap_in(upper_in);
-                                } else {
-                                    const int npd = st_pd[kk - 1] ^ 1;
-                                    bad |= !FT::fits(st_fl[kk - 1]);
-                                    pd_s[j] = npd; sz_s[j] = s - st_z[kk - 1];
-                                    const int upw = st_up[kk - 1];
-                                    fl_s[j] = (F)st_fl[kk - 1];
-                                    up_s[j] = FT::cap_in(upw == INT_MAX ? LLONG_MAX / 2 : (upw >= 0 ? (long long)upw : __ldg(P.upper + (npd >> 1))));
-                                }
-                            }
-                        }
+                // ---- cycle nodes: ChangeFlow (NS.cs:1012-1040) and the pred / succ_num part of UpdateTreeStructure (:1042-1183)
+                auto update_cycle_node = [&](int j, int x, int sz_u, int pd, int dp, bool hasF) {
+                    if (delta > 0) {
+                        const long long fl = new_flow((long long)fl_s[j], pd, hasF);
+                        bad |= !FT::fits(fl);
+                        fl_s[j] = (F)fl;
                     }
-                    if (change) {
+                    if (!change) return;
+                    if (hasF != in_side1) { sz_s[j] = sz_u + s; return; }               // v_in .. join (NS.cs:1174-1177)
+                    if (x < a) { sz_s[j] = sz_u - s; return; }                          // v_out .. join (NS.cs:1179-1182)
+                    // stem node kx (NS.cs:1095-1146): takes over the pred arc of the stem node below it, reversed
+                    if (x == a) P.flow[pd >> 1] = (out.zero & 1) ? 0 : FT::cap_out(up_s[j]);   // u_out: its pred arc leaves the tree at a bound
+                    const int kx = dp_uin - dp;
+                    if (kx == 0) {
+                        const long long nf = (lower_state ? 0 : upper_in) + val;
+                        bad |= !FT::fits(nf);
+                        pd_s[j] = in_arc * 2 + (dir_new_up ? 1 : 0); sz_s[j] = s;
+                        fl_s[j] = (F)nf; up_s[j] = FT::cap_in(upper_in);
+                    } else {
+                        int p_z, p_pd, p_up; long long p_fl;
+                        if (!longstem) { p_z = st_z[kx - 1]; p_pd = st_pd[kx - 1]; p_up = st_up[kx - 1]; p_fl = st_fl[kx - 1]; }
+                        else {
+                            int4 w[2];
+                            if (!poll_rec<2>(stem_g + (size_t)(ns - kx) * 2, seq, w, P)) sh.abort = 1;
+                            p_z = w[0].y; p_pd = w[0].z; p_fl = mk64(w[1].x, w[1].y); p_up = w[1].z;
+                        }
+                        const int npd = p_pd ^ 1;
+                        bad |= !FT::fits(p_fl);
+                        pd_s[j] = npd; sz_s[j] = s - p_z;
+                        fl_s[j] = (F)p_fl;
+                        up_s[j] = FT::cap_in(p_up == INT_MAX ? LLONG_MAX / 2 : (p_up >= 0 ? (long long)p_up : __ldg(P.upper + (npd >> 1))));
+                    }
+                };
+                if (nc <= kCandCap) {
+                    if (tid < nc) { const Cand c = sh.cl[tid]; update_cycle_node(c.j, c.in, c.sz, c.pd, c.dp, (c.zero & 2) != 0); }
+                } else {
+                    for (int j = tid; j < cntn; j += kTT) {
+                        const int x = in_s[j], sz_u = sz_s[j];
+                        const bool hasF = (unsigned)(inF - x) < (unsigned)sz_u;
+                        const bool hasS = (unsigned)(inS - x) < (unsigned)sz_u;
+                        if (hasF != hasS) update_cycle_node(j, x, sz_u, pd_s[j], dp_s[j], hasF);
+                    }
+                    __syncthreads();                                                    // the relabel pass below rewrites in_s
+                }
+                // ---- every node: re-label in[] in closed form; re-hung subtree: new depth and pi += sigma (NS.cs:1185-1209)
+                if (change) {
+                    const int base = b < a ? b + 1 : b - s + 1;                         // new index of u_in: first child of v_in
+                    const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
+                    const long long sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);   // NS.cs:1187-1188
+                    const int dshift = dp_vin + 1 - dp_uin;
+                    const int sh_lo = b < a ? b + 1 : a + s, sh_len = b < a ? a - b - 1 : b - a - s + 1, sh_by = b < a ? s : -s;
+                    for (int j = tid; j < cntn; j += kTT) {
+                        const int x = in_s[j];
                         if ((unsigned)(x - a) < (unsigned)s) {
-                            int off;
+                            int off, l = 0;
                             if (ns == 1) off = x - a;
                             else {
-                                int l = 0, r = ns - 1;                                  // smallest k with x inside subtree(stem k)
-                                while (l < r) { const int mid = (l + r) >> 1; if ((unsigned)(x - st_in[mid]) < (unsigned)st_z[mid]) r = mid; else l = mid + 1; }
-                                if (l == 0) off = x - st_in[0];
+                                int r = ns - 1, l_in, l_z;                              // smallest l with x inside subtree(stem l)
+                                while (l < r) { const int mid = (l + r) >> 1; stem_io(mid, l_in, l_z); if ((unsigned)(x - l_in) < (unsigned)l_z) r = mid; else l = mid + 1; }
+                                stem_io(l, l_in, l_z);
+                                if (l == 0) off = x - l_in;
                                 else {
-                                    int rr = x - st_in[l];
-                                    if (x > st_in[l - 1]) rr -= st_z[l - 1];
-                                    off = st_z[l - 1] + rr;
+                                    int p_in, p_z; stem_io(l - 1, p_in, p_z);
+                                    int rr = x - l_in;
+                                    if (x > p_in) rr -= p_z;
+                                    off = p_z + rr;
                                 }
                             }
-                            const int nx = base + off;
-                            in_s[j] = nx;
+                            const int nx = base + off, nd = dp_s[j] + dshift + 2 * l;
+                            in_s[j] = nx; dp_s[j] = nd;
                             atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)sigma);
-                            P.node[lo + j].in = nx;
-                        } else if (b < a) {
-                            if (x > b && x < a) { in_s[j] = x + s; P.node[lo + j].in = x + s; }
-                        } else {
-                            if (x >= a + s && x <= b) { in_s[j] = x - s; P.node[lo + j].in = x - s; }
+                            *reinterpret_cast<int2*>(&P.node[lo + j].in) = make_int2(nx, nd);
+                        } else if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {
+                            in_s[j] = x + sh_by; P.node[lo + j].in = x + sh_by;
                         }
                     }
                 }
@@ -800,6 +794,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 // hop 3: everything this CTA wrote for pivot k is visible before DONE(k)
                 PROBE(13);
                 __syncthreads();
+                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (tid == 0) { __threadfence(); st_vol_u32(P.done + (size_t)cta * 32, (unsigned)k); }
                 PROBE(14);
             }
@@ -861,7 +856,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 // ------------------------------------------------------------------------------------------------ launchers
 
 namespace {
-constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 5 * 4);
+constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
 constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (8 + 4 * 4);
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace

@@ -236,6 +236,25 @@ def test_netgen8_full_size_against_recorded_oracle(k):
     assert bad == 0 and dual == g["total_cost"]
 
 
+@pytest.mark.parametrize("rows", [256, 1024])
+def test_grid_time_expanded_full_size_against_recorded_oracle(rows):
+    """BASELINE.json config 4: rows x rows time-expanded grid (deep trees, long cycles and stems), full solve against the
+    recorded CPU-oracle result (tests/golden/large.json) + the optimality check."""
+    p = instances.grid_time_expanded(rows, rows)
+    g = _large(p.name)
+    if g is None:
+        pytest.skip("no recorded oracle result for this size")
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ns.SetOptimizationConfig(mcf.OptimizationConfig())
+    assert ns.Solve() == mcf.SolverStatus.Optimal
+    assert ns.GetMetrics().iterations == g["pivots"]
+    assert ns.GetTotalCost() == g["total_cost"]
+    assert hashlib.sha256(ns.flows().tobytes()).hexdigest() == g["flow_sha256"]
+    assert hashlib.sha256(ns.potentials().tobytes()).hexdigest() == g["pi_sha256"]
+    bad, dual = oracle.validate(p, ns.flows(), ns.potentials(), ns.GetTotalCost())
+    assert bad == 0 and dual == g["total_cost"]
+
+
 def test_best_eligible_prefix_at_2_16():
     """Best Eligible on 2^16 nodes for a bounded number of pivots: same pivot count and (via a full small solve above)
     the same tie-break; a full BE solve at this size is hours of CPU."""
