@@ -1,0 +1,134 @@
+// CudaNetworkSimplex.cs - the reference-side binding of libmcfgpu.so: a drop-in IMinCostFlowSolver
+// (src/MinCostFlow.Core/IMinCostFlowSolver.cs:8-34) with the NetworkSimplex setter surface
+// (src/MinCostFlow.Core/Lemon/Algorithms/NetworkSimplex.cs:153-210, :470-587).
+// NOT compiled in this repository's image (no dotnet); it is the file a maintainer adds to MinCostFlow.Core.
+// Blittable structs mirror include/mcfgpu.h field for field.
+using System;
+using System.Runtime.InteropServices;
+using MinCostFlow.Core.Lemon.Algorithms;
+using MinCostFlow.Core.Lemon.Graphs;
+using MinCostFlow.Core.Lemon.Types;
+
+namespace MinCostFlow.Core.Cuda
+{
+    [StructLayout(LayoutKind.Sequential)]
+    public struct McfOptimizationConfig
+    {
+        public int Flags, MaxBlockSize, MinBlockSize, DenseNetworkThreshold, ConsecutiveHitsBeforeAdapt, Reserved0;
+        public double CandidateListRatio, BlockSizeGrowthFactor, BlockSizeShrinkFactor, LowHitRateThreshold, HighHitRateThreshold, MinBlockSizeRatio;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct McfOptions
+    {
+        public int SupplyType, PivotRule, AutoConfiguration, OptimizedPivot, Device, MaxCtas, LookaheadBlocks, Engine;
+        public long StopAfterPivots;
+        public double BarrierTimeoutSeconds;
+        public McfOptimizationConfig Config;
+    }
+
+    internal static unsafe class Native
+    {
+        private const string Lib = "mcfgpu";   // libmcfgpu.so
+        [DllImport(Lib)] internal static extern int mcf_create(int n, int m, int* source, int* target, out IntPtr handle);
+        [DllImport(Lib)] internal static extern void mcf_destroy(IntPtr h);
+        [DllImport(Lib)] internal static extern void mcf_default_options(out McfOptions o);
+        [DllImport(Lib)] internal static extern int mcf_set_arcs(IntPtr h, long* lower, long* upper, long* cost);
+        [DllImport(Lib)] internal static extern int mcf_set_supply(IntPtr h, long* supply);
+        [DllImport(Lib)] internal static extern int mcf_set_options(IntPtr h, ref McfOptions o);
+        [DllImport(Lib)] internal static extern int mcf_solve(IntPtr h, out int status);
+        [DllImport(Lib)] internal static extern int mcf_get_flows(IntPtr h, long* outM);
+        [DllImport(Lib)] internal static extern int mcf_get_potentials(IntPtr h, long* outN);
+        [DllImport(Lib)] internal static extern int mcf_get_total_cost(IntPtr h, out long cost);
+        [DllImport(Lib)] internal static extern IntPtr mcf_last_error(IntPtr h);
+    }
+
+    /// <summary>NetworkSimplex on a B200 through libmcfgpu.so.  Same results, bit for bit, as NetworkSimplex.Solve().</summary>
+    public sealed unsafe class CudaNetworkSimplex : IMinCostFlowSolver, IDisposable
+    {
+        private readonly IGraph _graph;
+        private readonly int _n, _m;
+        private readonly long[] _lower, _upper, _cost, _supply;
+        private long[] _flow = Array.Empty<long>(), _pi = Array.Empty<long>();
+        private long _totalCost;
+        private McfOptions _opt;
+        private IntPtr _h;
+        public SolverStatus Status { get; private set; } = SolverStatus.NotSolved;
+
+        public CudaNetworkSimplex(IGraph graph)
+        {
+            _graph = graph ?? throw new ArgumentNullException(nameof(graph));          // NetworkSimplex.cs:121
+            _n = graph.NodeCount; _m = graph.ArcCount;
+            var src = new int[_m]; var tgt = new int[_m];
+            for (int e = 0; e < _m; e++) { src[e] = graph.Source(new Arc(e)).Id; tgt[e] = graph.Target(new Arc(e)).Id; }   // NetworkSimplex.cs:605-613
+            _lower = new long[_m]; _upper = new long[_m]; _cost = new long[_m]; _supply = new long[_n];
+            Array.Fill(_upper, long.MaxValue / 2);                                         // INF, NetworkSimplex.cs:127, :616
+            Native.mcf_default_options(out _opt);
+            fixed (int* s = src, t = tgt) Check(Native.mcf_create(_n, _m, s, t, out _h));
+        }
+
+        public CudaNetworkSimplex SetArcBounds(Arc arc, long lower, long upper) { CheckArc(arc); _lower[arc.Id] = lower; _upper[arc.Id] = upper; return this; }
+        public CudaNetworkSimplex SetArcCost(Arc arc, long cost) { CheckArc(arc); _cost[arc.Id] = cost; return this; }
+        public CudaNetworkSimplex SetNodeSupply(Node node, long supply) { if (!_graph.IsValidNode(node)) throw new ArgumentException("Invalid node"); _supply[node.Id] = supply; return this; }
+        public CudaNetworkSimplex SetSupplyType(SupplyType type) { _opt.SupplyType = (int)type; return this; }
+        public CudaNetworkSimplex SetPivotRule(PivotRule rule) { _opt.PivotRule = (int)rule; return this; }
+        public void EnableOptimizedPivot(bool enable = true) => _opt.OptimizedPivot = enable ? 1 : 0;
+        public void SetAutoConfiguration(bool enable) => _opt.AutoConfiguration = enable ? 1 : 0;
+        public void SetOptimizationConfig(OptimizationConfig c)
+        {
+            _opt.Config = new McfOptimizationConfig {
+                Flags = (int)c.Flags, MaxBlockSize = c.MaxBlockSize, MinBlockSize = c.MinBlockSize, DenseNetworkThreshold = c.DenseNetworkThreshold,
+                ConsecutiveHitsBeforeAdapt = c.ConsecutiveHitsBeforeAdapt, CandidateListRatio = c.CandidateListRatio,
+                BlockSizeGrowthFactor = c.BlockSizeGrowthFactor, BlockSizeShrinkFactor = c.BlockSizeShrinkFactor,
+                LowHitRateThreshold = c.LowHitRateThreshold, HighHitRateThreshold = c.HighHitRateThreshold, MinBlockSizeRatio = c.MinBlockSizeRatio };
+            _opt.AutoConfiguration = 0;                                                    // NetworkSimplex.cs:560
+        }
+
+        public SolverStatus Solve()
+        {
+            if (_opt.PivotRule > (int)PivotRule.BlockSearch) throw new NotImplementedException($"Pivot rule {(PivotRule)_opt.PivotRule} not implemented yet");   // NetworkSimplex.cs:884
+            fixed (long* lo = _lower, up = _upper, co = _cost, su = _supply)               // pinned for the call only, like OptimizedPivotWrapper (NetworkSimplex.cs:1699-1722)
+            {
+                Check(Native.mcf_set_arcs(_h, lo, up, co));
+                Check(Native.mcf_set_supply(_h, su));
+            }
+            Check(Native.mcf_set_options(_h, ref _opt));
+            Check(Native.mcf_solve(_h, out int st));
+            Status = (SolverStatus)st;
+            if (Status == SolverStatus.Optimal)
+            {
+                _flow = new long[_m]; _pi = new long[_n];
+                fixed (long* f = _flow, p = _pi) { Check(Native.mcf_get_flows(_h, f)); Check(Native.mcf_get_potentials(_h, p)); }
+                Check(Native.mcf_get_total_cost(_h, out _totalCost));
+            }
+            return Status;
+        }
+
+        public long GetFlow(Arc arc) { RequireOptimal(); CheckArc(arc); return _flow[arc.Id]; }               // NetworkSimplex.cs:416-431
+        public long GetPotential(Node node) { RequireOptimal(); if (!_graph.IsValidNode(node)) throw new ArgumentException("Invalid node"); return _pi[node.Id]; }
+        public long GetTotalCost() { RequireOptimal(); return _totalCost; }
+
+        private void RequireOptimal() { if (Status != SolverStatus.Optimal) throw new InvalidOperationException("Solution not optimal"); }
+        private void CheckArc(Arc arc) { if (!_graph.IsValidArc(arc)) throw new ArgumentException("Invalid arc"); }
+        private void Check(int rc)
+        {
+            if (rc == 0) return;
+            string msg = _h != IntPtr.Zero ? Marshal.PtrToStringAnsi(Native.mcf_last_error(_h)) ?? "" : "";
+            throw rc switch { -1 => new ArgumentException(msg), -5 => new InvalidOperationException("Solution not optimal"),
+                              -2 => new PlatformNotSupportedException("no sm_100 CUDA device (libmcfgpu has no CPU fallback)"),
+                              _ => new ExternalException($"libmcfgpu error {rc}: {msg}") };
+        }
+        public void Dispose() { if (_h != IntPtr.Zero) { Native.mcf_destroy(_h); _h = IntPtr.Zero; } }
+    }
+
+    /// <summary>The README-style fluent facade (README.md:48-60) over the real surface.</summary>
+    public static class NetworkSimplexFacade
+    {
+        public static CudaNetworkSimplex SupplyMap(this CudaNetworkSimplex s, Func<Node, long> supply, IGraph g)
+        { for (int i = 0; i < g.NodeCount; i++) s.SetNodeSupply(new Node(i), supply(new Node(i))); return s; }
+        public static SolverStatus Run(this CudaNetworkSimplex s) => s.Solve();
+        public static long Flow(this CudaNetworkSimplex s, Arc a) => s.GetFlow(a);
+        public static long Potential(this CudaNetworkSimplex s, Node n) => s.GetPotential(n);
+        public static long TotalCost(this CudaNetworkSimplex s) => s.GetTotalCost();
+    }
+}
