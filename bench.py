@@ -149,6 +149,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import mincostflow_b200 as mcf
+    from mincostflow_b200 import batch
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -183,13 +184,13 @@ def run_ours(args):
         piv = kus = h2d = d2h = 0
         launches = 0
         res = []
-        for ns in solvers:
+        for i, ns in enumerate(solvers):
             ns._dirty = True                                   # host buffers are marshalled and uploaded again every step
             st = ns.Solve()
             M = ns.GetMetrics()
             assert st == mcf.SolverStatus.Optimal, st
             piv += M.iterations; kus += M.kernel_time_us; h2d += M.h2d_bytes; d2h += M.d2h_bytes; launches += 1
-            res.append((int(st), M.iterations, ns.GetTotalCost(), int(ns.flows().sum()), int(ns.potentials().sum())))
+            res.append(batch.make_record(rank * per + i, int(st), M.iterations, ns.GetTotalCost(), ns.flows(), ns.potentials()))
         return piv, kus, launches, h2d, d2h, res
 
     for _ in range(args.warmup):
@@ -203,9 +204,9 @@ def run_ours(args):
         piv, kus, launches, h2d, d2h, last = step()
         tot_piv += piv; tot_kus += kus; tot_h2d += h2d; tot_d2h += d2h; tot_launch += launches
         if dist is not None:                                   # NCCL gather of the result records on rank 0
-            rec = torch.tensor(last, dtype=torch.int64, device=dev)
-            gathered = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
-            dist.gather(rec, gathered, dst=0)
+            gathered = batch.gather_records(last, world * per, dist=dist, device=dev)
+            if rank == 0:
+                assert (gathered[:, 1] == 1).all(), gathered
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
