@@ -344,7 +344,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
     CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
-    CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)team * 32));
+    CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)(team + pricers) * 32));     // DONE flags of the owners + GATHERED flags of the pricers
     const size_t w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
     const size_t seg_off = (2 * w_pr + w_late + 2 * w_cyc + 7) & ~(size_t)7;
@@ -360,7 +360,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4));
     CUDA_TRY(h, up(h->d_node.p, h->h_node.data(), (size_t)(n + 1) * sizeof(mcf::NodeRec)));
     CUDA_TRY(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(mcf::Ctl), st));
-    CUDA_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)team * 32 * sizeof(unsigned), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)(team + pricers) * 32 * sizeof(unsigned), st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_mail.p, 0, (seg_off + w_seg + 8) * sizeof(int4), st));
     h->metrics.h2d_bytes = bytes;
     std::memset(P, 0, sizeof(*P));

@@ -127,7 +127,7 @@ struct TeamParams {
     int4* cyc;                                           // [2][team][kMailWords]     owner -> all
     int4* stemhdr;                                       // [2][team][kMailWords]     owner -> all (stem exchange)
     int4* stemseg;                                       // [2][n+1][2]               stem entries, owner o at its slice offset
-    unsigned int* done;                                  // [team][32]                owner -> pricers
+    unsigned int* done;                                  // [team + pricers][32]      owner -> pricers (DONE), pricer -> owners (GATHERED)
     Ctl* ctl;
     int team;                                            // CTAs: [0, pricers) price, [pricers, team) own node slices
     int pricers;

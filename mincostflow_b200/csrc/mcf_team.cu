@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
-constexpr int kPf = 8;                                  // arcs per pricer thread staged ahead
+constexpr int kPf = 4;                                  // arcs per pricer thread staged ahead (2048 per pricing CTA)
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
 __device__ __forceinline__ int4 ld_vol4(const int4* p)
@@ -102,8 +102,16 @@ struct Book {                       // statistics and timers: touched by thread 
     int cons_low, cons_high;
 };
 
+struct Pending {                    // one pivot's update in closed form: what the pricers replay on staged node records
+    int valid, change;
+    int a, s, b;                    // re-hung subtree = old interval [a, a+s); b = in[v_in]
+    int ns, longstem, dshift, par, seq;
+    long long sigma;
+};
+
 struct TeamShared {
     Book bk;
+    Pending pend;
     Cand cl[kCandCap];              // cycle-node candidates of this slice (owner scan)
     Cand wc[2][kTW];                // per-warp winners (hop 2 gather, owner slow path)
     PWin pw[kTW];                   // per-warp pricing winners
@@ -223,12 +231,19 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const sz_s = in_s + P.slice;
     int* const pd_s = sz_s + P.slice;
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
-    // pricers
-    long long* const pf_up = reinterpret_cast<long long*>(body);                // [kPf * kTT]
-    int* const pf_src = reinterpret_cast<int*>(pf_up + kPf * kTT);
-    int* const pf_tgt = pf_src + kPf * kTT;
-    int* const pf_cost = pf_tgt + kPf * kTT;
-    int* const pf_st = pf_cost + kPf * kTT;
+    // pricers: arc data and both ends' node records of this pricer's share of the staged block
+    constexpr int kStage = kPf * kTT;
+    long long* const pf_up = reinterpret_cast<long long*>(body);
+    long long* const pf_pis = pf_up + kStage;
+    long long* const pf_pit = pf_pis + kStage;
+    int* const pf_src = reinterpret_cast<int*>(pf_pit + kStage);
+    int* const pf_tgt = pf_src + kStage;
+    int* const pf_cost = pf_tgt + kStage;
+    int* const pf_st = pf_cost + kStage;
+    int* const pf_ins = pf_st + kStage;
+    int* const pf_int = pf_ins + kStage;
+    int* const pf_dps = pf_int + kStage;
+    int* const pf_dpt = pf_dps + kStage;
 
     int status = ST_NOT_SOLVED;
     {
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
         }
-        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; }
+        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; sh.pend.valid = 0; }
         if (__syncthreads_or(bad)) { if (tid == 0) P.ctl->needs_wide = 1; }
     }
     if (tid == 0) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
@@ -249,10 +264,100 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     // pricer state (BlockSearchPivot fields, NS.cs:1294-1302); identical in every pricer
     int next_arc = 0, B = P.block_size;
     int pf_next = -1, pf_B = 0;                          // what is staged: this pricer's share of block [pf_next, pf_next + pf_B)
-    int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0;   // state changes decided after the staging loads
+    long long pf_upto = 0;                               // ... as of "all updates of pivots <= pf_upto applied"
+    long long done_seen = 0;                             // DONE(j) observed from every owner for all j <= done_seen
+    // arc-state changes of the last two pivots: applied on top of whatever a scan reads (staged or global), newest first, so a
+    // scan never depends on how fast this CTA's own state[] stores become visible to its other warps
+    int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0, patch2_arc0 = -1, patch2_st0 = 0, patch2_arc1 = -1, patch2_st1 = 0;
+    auto fix_state = [&](int idx, int st) -> int {
+        return idx == patch_arc0 ? patch_st0 : idx == patch_arc1 ? patch_st1 : idx == patch2_arc0 ? patch2_st0 : idx == patch2_arc1 ? patch2_st1 : st;
+    };
     long long iterations = 0;
 #define PROBE(i) do { if (tid == 0 && ((i) < 8 ? cta == 0 : cta == NP)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
 #define TICK(acc) do { if (cta == 0 && tid == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
+
+    // pricers: wait until every owner's updates of pivots <= j are visible (hop 3); CTA-uniform, false = abandoned
+    auto wait_done = [&](long long j) -> bool {
+        if (done_seen >= j) return true;
+        if (tid < nown) {
+            const unsigned want = (unsigned)j;
+            const unsigned* p = P.done + (size_t)(NP + tid) * 32;
+            unsigned spins = 0; long long t0 = 0;
+            while ((int)(ld_vol_u32(p) - want) < 0) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+        }
+        __syncthreads();
+        done_seen = j;
+        return sh.abort == 0;
+    };
+    // this pricer's share [s_lo, s_hi) of the block of `bsz` arcs that starts at the cursor
+    auto share = [&](int bsz, int& s_lo, int& s_hi) -> bool {
+        const int blk0 = bsz < S ? bsz : S;
+        const int seg = (blk0 + NP - 1) / NP;
+        s_lo = cta * seg; s_hi = min(blk0, s_lo + seg);
+        return seg <= kStage;
+    };
+    // stage the arc data of the share (streams from DRAM; independent of the basis except `state`, which is patched later)
+    auto stage_static = [&](int cursor, int s_lo, int s_hi) {
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) {
+            const int q = tid + j * kTT, off = s_lo + q;
+            if (off < s_hi) {
+                int idx = cursor + off; if (idx >= S) idx -= S;
+                pf_src[q] = __ldg(P.src + idx); pf_tgt[q] = __ldg(P.tgt + idx); pf_cost[q] = __ldg(P.cost + idx);
+                pf_st[q] = __ldcg(P.state + idx); pf_up[q] = __ldg(P.upper + idx);
+            }
+        }
+    };
+    // gather both ends' node records {pi, in, depth} of the staged share from the mirror
+    auto stage_gather = [&](int s_lo, int s_hi) {
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) {
+            const int q = tid + j * kTT, off = s_lo + q;
+            if (off < s_hi) {
+                const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + pf_src[q]));
+                const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + pf_tgt[q]));
+                pf_pis[q] = mk64(rs.x, rs.y); pf_ins[q] = rs.z; pf_dps[q] = rs.w;
+                pf_pit[q] = mk64(rt.x, rt.y); pf_int[q] = rt.z; pf_dpt[q] = rt.w;
+            }
+        }
+    };
+    // closed-form re-labelling of one node by the update described in `U` (UpdateTreeStructure seen through in[] / depth):
+    // nodes of the re-hung subtree [a, a+s) get their new place under v_in, nodes between the old and new place shift by s
+    auto relabel = [&](const Pending& U, int x, int dp, int& nx, int& ndp) -> bool {
+        const int4* const stem_g = P.stemseg + (size_t)U.par * (n + 1) * 2;
+        auto stem_io = [&](int kx, int& o_in, int& o_z) {
+            if (!U.longstem) { o_in = st_in[kx]; o_z = st_z[kx]; }
+            else { int4 w; if (!poll_word(stem_g + (size_t)(U.ns - 1 - kx) * 2, U.seq, w, P)) sh.abort = 1; o_in = w.x; o_z = w.y; }
+        };
+        nx = x; ndp = dp;
+        if ((unsigned)(x - U.a) < (unsigned)U.s) {
+            int off, l = 0;
+            if (U.ns == 1) off = x - U.a;
+            else {
+                int r = U.ns - 1, l_in, l_z;                                    // smallest l with x inside subtree(stem l)
+                while (l < r) { const int mid = (l + r) >> 1; stem_io(mid, l_in, l_z); if ((unsigned)(x - l_in) < (unsigned)l_z) r = mid; else l = mid + 1; }
+                stem_io(l, l_in, l_z);
+                if (l == 0) off = x - l_in;
+                else {
+                    int p_in, p_z; stem_io(l - 1, p_in, p_z);
+                    int rr = x - l_in;
+                    if (x > p_in) rr -= p_z;
+                    off = p_z + rr;
+                }
+            }
+            nx = (U.b < U.a ? U.b + 1 : U.b - U.s + 1) + off;                   // u_in becomes the first child of v_in
+            ndp = dp + U.dshift + 2 * l;
+            return true;
+        }
+        const int sh_lo = U.b < U.a ? U.b + 1 : U.a + U.s, sh_len = U.b < U.a ? U.a - U.b - 1 : U.b - U.a - U.s + 1;
+        if ((unsigned)(x - sh_lo) < (unsigned)sh_len) nx = x + (U.b < U.a ? U.s : -U.s);
+        return false;
+    };
+
+    if (pricer) {                                        // stage the very first block; the initial basis is what the host uploaded
+        int s_lo, s_hi;
+        if (share(B, s_lo, s_hi)) { stage_static(0, s_lo, s_hi); stage_gather(s_lo, s_hi); pf_next = 0; pf_B = B; pf_upto = 0; }
+    }
 
     for (;;) {
         const long long k = iterations + 1;
@@ -261,85 +366,81 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         bool have_win = false;                            // sh.win holds the entering arc
         int search_end = 0;                               // pricers: scan offset just past the winning block
 
-        // ================================================================ pricers: wait DONE(k-1), price their share, post
+        // ================================================================ pricers: price their share of the first block, post
         if (pricer) {
-            if (k > 1) {
-                if (tid < nown) {
-                    const unsigned want = (unsigned)(k - 1);
-                    const unsigned* p = P.done + (size_t)(NP + tid) * 32;
-                    unsigned spins = 0; long long t0 = 0;
-                    while (ld_vol_u32(p) != want) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                }
-                __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            }
             TICK(t_wdone);
             PROBE(0);
-
-            // ---- round 0 of BlockSearchPivot.FindEnteringArc (NS.cs:1339-1397): the first block, split over the pricers
-            const int blk0 = B < S ? B : S;
-            const int seg = (blk0 + NP - 1) / NP;
-            const int s_lo = cta * seg, s_hi = min(blk0, s_lo + seg);
+            // ---- round 0 of BlockSearchPivot.FindEnteringArc (NS.cs:1339-1397): the first block, split over the pricers.
+            // The share was staged (arc data + both ends' node records) BEFORE the previous pivot's update was applied; that
+            // one update is replayed here from its closed form (sh.pend), so pricing does not wait for hop 3.
+            int s_lo, s_hi;
+            const bool fits = share(B, s_lo, s_hi);
             PWin best = pwin_none();
-            const bool staged = pf_next == next_arc && pf_B == B && seg <= kPf * kTT;
-            if (staged) {
+            if (fits) {
+                if (!(pf_next == next_arc && pf_B == B)) {               // nothing usable staged (first use of a new block size): stage now
+                    if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    stage_static(next_arc, s_lo, s_hi); stage_gather(s_lo, s_hi);
+                    pf_next = next_arc; pf_B = B; pf_upto = k - 1;
+                }
+                const bool replay = pf_upto < k - 1;                     // exactly update k-1 is missing from the staged records
+                const Pending U = sh.pend;
+                int bq = -1;
 #pragma unroll
-                for (int jb = 0; jb < kPf; jb += 4) {
-                    if (s_lo + jb * kTT >= s_hi) break;
-                    int4 rs[4], rt[4];
-                    int st[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int q = tid + (jb + j) * kTT, off = s_lo + q;
-                        if (off < s_hi) {
-                            int idx = next_arc + off; if (idx >= S) idx -= S;
-                            rs[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_src[q]));
-                            rt[j] = __ldcg(reinterpret_cast<const int4*>(P.node + pf_tgt[q]));
-                            st[j] = idx == patch_arc0 ? patch_st0 : (idx == patch_arc1 ? patch_st1 : pf_st[q]);
+                for (int j = 0; j < kPf; ++j) {
+                    const int q = tid + j * kTT, off = s_lo + q;
+                    if (off < s_hi) {
+                        int idx = next_arc + off; if (idx >= S) idx -= S;
+                        const int st = fix_state(idx, pf_st[q]);
+                        long long ps = pf_pis[q], pt = pf_pit[q];
+                        if (replay && U.change) {                        // UpdatePotentials of the pending pivot (NS.cs:1185-1209)
+                            if ((unsigned)(pf_ins[q] - U.a) < (unsigned)U.s) ps += U.sigma;
+                            if ((unsigned)(pf_int[q] - U.a) < (unsigned)U.s) pt += U.sigma;
                         }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int q = tid + (jb + j) * kTT, off = s_lo + q;
-                        if (off < s_hi) {
-                            const long long ps = mk64(rs[j].x, rs[j].y), pt = mk64(rt[j].x, rt[j].y);
-                            const int c = pf_cost[q];
-                            const long long rc = (long long)st[j] * ((long long)c + ps - pt);
-                            if (rc < best.rc) {
-                                best.rc = rc; best.off = off; best.src = pf_src[q]; best.tgt = pf_tgt[q]; best.cost = c; best.state = st[j];
-                                best.in_s = rs[j].z; best.in_t = rt[j].z; best.dp_s = rs[j].w; best.dp_t = rt[j].w; best.pi_s = ps; best.pi_t = pt; best.upper = pf_up[q];
-                            }
-                        }
+                        const long long rc = (long long)st * ((long long)pf_cost[q] + ps - pt);
+                        if (rc < best.rc) { best.rc = rc; best.off = off; best.arc = idx; best.state = st; best.pi_s = ps; best.pi_t = pt; bq = q; }
                     }
                 }
+                const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
+                if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
+                else if (lane == wl) {
+                    best.src = pf_src[bq]; best.tgt = pf_tgt[bq]; best.cost = pf_cost[bq]; best.upper = pf_up[bq];
+                    best.in_s = pf_ins[bq]; best.in_t = pf_int[bq]; best.dp_s = pf_dps[bq]; best.dp_t = pf_dpt[bq];
+                    if (replay && U.change) {                            // the winner's labels as they are after the pending update
+                        int nx, nd;
+                        relabel(U, best.in_s, best.dp_s, nx, nd); best.in_s = nx; best.dp_s = nd;
+                        relabel(U, best.in_t, best.dp_t, nx, nd); best.in_t = nx; best.dp_t = nd;
+                    }
+                    sh.pw[warp] = best;
+                }
             } else {
+                // share larger than the staging area (B > pricers x 2048): price straight from global memory
+                if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 for (int off = s_lo + tid; off < s_hi; off += kTT) {
                     int idx = next_arc + off; if (idx >= S) idx -= S;
                     const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
-                    const int st = __ldcg(P.state + idx);
+                    const int st = fix_state(idx, __ldcg(P.state + idx));
                     const long long up = __ldg(P.upper + idx);
                     const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + s));
                     const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + t));
                     const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
                     const long long rc = (long long)st * ((long long)c + ps - pt);
                     if (rc < best.rc) {
-                        best.rc = rc; best.off = off; best.src = s; best.tgt = t; best.cost = c; best.state = st;
+                        best.rc = rc; best.off = off; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
                         best.in_s = rs.z; best.in_t = rt.z; best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt; best.upper = up;
                     }
                 }
-            }
-            {   // CTA arg-min of (rc, off): warp stage, then warp 0 reduces the kTW warp winners and posts the record
                 const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
                 if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
-                else if (lane == wl) { int idx = next_arc + best.off; if (idx >= S) idx -= S; best.arc = idx; sh.pw[warp] = best; }
-                __syncthreads();
-                if (warp == 0) {
-                    const PWin* q = &sh.pw[lane & (kTW - 1)];
-                    const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
-                    PWin mine = pwin_none();
-                    if (ww >= 0) mine = sh.pw[ww];
-                    if (lane < 7) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
-                }
+                else if (lane == wl) sh.pw[warp] = best;
+            }
+            __syncthreads();
+            if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            if (warp == 0) {                                             // CTA arg-min of (rc, off) over the warp winners, post the record
+                const PWin* q = &sh.pw[lane & (kTW - 1)];
+                const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
+                PWin mine = pwin_none();
+                if (ww >= 0) mine = sh.pw[ww];
+                if (lane < 7) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
             }
             PROBE(1);
         }
@@ -368,7 +469,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         }
         if (!have_win) {
             if (pricer) {
-                // ---- later rounds: pricer p prices block 1 + (r-1)*NP + p; the lowest block with a negative reduced cost wins
+                // ---- later rounds: pricer p prices block 1 + (r-1)*NP + p straight from global memory (every update visible first);
+                // the lowest block with a negative reduced cost wins
+                if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 const long long nblk = ((long long)S + B - 1) / B;
                 int found_blk = -1;
                 for (int r = 1; found_blk < 0; ++r) {
@@ -381,7 +484,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         for (long long off = o_lo + tid; off < o_hi; off += kTT) {
                             int idx = next_arc + (int)off; if (idx >= S) idx -= S;
                             const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
-                            const int st = __ldcg(P.state + idx);
+                            const int st = fix_state(idx, __ldcg(P.state + idx));
                             const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + s));
                             const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + t));
                             const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
@@ -402,7 +505,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
                         PWin mine = pwin_none();
                         if (ww >= 0) mine = sh.pw[ww];
-                        // words 0, 2..5 first, one fence, then word 1 (which carries the round) as the flag: a round record
+                        // words 0, 2..6 first, one fence, then word 1 (which carries the round) as the flag: a round record
                         // reuses the slot of round r-2 of the same pivot, so the sequence number alone cannot validate it
                         int4* const dst = P.prc + ((size_t)(r & 1) * NP + cta) * kMailWords;
                         if (lane < 7 && lane != 1) post_pwin(dst, mine, r, seq, lane);
@@ -476,23 +579,16 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
 
         if (pricer) {
-            // ---- stage this pricer's share of the next pivot's first block: arc data streams from DRAM while hops 2..3 are in flight
-            const int blk0 = B < S ? B : S;
-            const int seg = (blk0 + NP - 1) / NP;
-            if (seg <= kPf * kTT) {
-                const int s_lo = cta * seg, s_hi = min(blk0, s_lo + seg);
-#pragma unroll
-                for (int j = 0; j < kPf; ++j) {
-                    const int q = tid + j * kTT, off = s_lo + q;
-                    if (off < s_hi) {
-                        int idx = next_arc + off; if (idx >= S) idx -= S;
-                        pf_src[q] = __ldg(P.src + idx); pf_tgt[q] = __ldg(P.tgt + idx); pf_cost[q] = __ldg(P.cost + idx);
-                        pf_st[q] = __ldcg(P.state + idx); pf_up[q] = __ldg(P.upper + idx);
-                    }
-                }
-                pf_next = next_arc; pf_B = B;
-            } else pf_next = -1;
-            patch_arc0 = patch_arc1 = -1;
+            // ---- stage this pricer's share of the NEXT pivot's first block.  Arc data streams from DRAM right away; the node
+            // records are gathered once every update up to pivot k-1 is visible (hop 3 of the previous pivot, off the critical
+            // path) and BEFORE any owner applies update k: owners wait for GATHERED(k+1) below.  Update k is replayed at pricing.
+            int s_lo, s_hi;
+            const bool fits = share(B, s_lo, s_hi);
+            if (fits) stage_static(next_arc, s_lo, s_hi);
+            if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            if (fits) { stage_gather(s_lo, s_hi); pf_next = next_arc; pf_B = B; pf_upto = k - 1; } else pf_next = -1;
+            __syncthreads();
+            if (tid == 0) st_vol_u32(P.done + (size_t)(G + cta) * 32, (unsigned)(k + 1));      // GATHERED(k+1)
             PROBE(3);
         } else PROBE(9);
 
@@ -680,7 +776,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         }
                     }
                 }
-                if (!longstem && !pricer) {
+                if (!longstem) {
                     for (int q = tid; q < ns; q += kTT) {
                         int4 w[2];
                         if (!poll_rec<2>(stem_g + (size_t)q * 2, seq, w, P)) sh.abort = 1;
@@ -692,24 +788,36 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
                 TICK(t_stem);
             }
-            // stem accessors: shared memory, or (stems longer than the staging area) the published entries themselves
-            auto stem_io = [&](int kx, int& o_in, int& o_z) {
-                if (!longstem) { o_in = st_in[kx]; o_z = st_z[kx]; }
-                else { int4 w; if (!poll_word(stem_g + (size_t)(ns - 1 - kx) * 2, seq, w, P)) sh.abort = 1; o_in = w.x; o_z = w.y; }
-            };
             if (change && tid == 0) { if (ns > sh.bk.max_stem) sh.bk.max_stem = ns; sh.bk.moved_nodes += s; }
 
             // ================================================================ updates
             const bool dir_new_up = u_in == a_src;                                      // NS.cs:1143
+            const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
+            Pending U;                                                                  // this pivot's update in closed form
+            U.valid = 1; U.change = change ? 1 : 0; U.a = a; U.s = s; U.b = b; U.ns = ns; U.longstem = longstem ? 1 : 0;
+            U.dshift = dp_vin + 1 - dp_uin; U.par = par; U.seq = seq;
+            U.sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);              // NS.cs:1187-1188
             if (pricer) {
                 // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them; every pricer keeps its own view
+                patch2_arc0 = patch_arc0; patch2_st0 = patch_st0; patch2_arc1 = patch_arc1; patch2_st1 = patch_st1;
                 if (change) { patch_arc0 = in_arc; patch_st0 = STATE_TREE; patch_arc1 = out.pd >> 1; patch_st1 = (out.zero & 1) ? STATE_LOWER : STATE_UPPER; }
                 else { patch_arc0 = in_arc; patch_st0 = -a_state; patch_arc1 = -1; }
                 if (tid == 0) {
                     P.state[patch_arc0] = patch_st0;
                     if (patch_arc1 >= 0) P.state[patch_arc1] = patch_st1;
+                    sh.pend = U;                                                        // replayed by the next pricing (see above)
                 }
+                __syncthreads();
             } else {
+                // update k may touch the mirror only after every pricer has gathered the next block's node records
+                if (tid < NP) {
+                    const unsigned want = (unsigned)(k + 1);
+                    const unsigned* p = P.done + (size_t)(G + tid) * 32;
+                    unsigned spins = 0; long long t0 = 0;
+                    while ((int)(ld_vol_u32(p) - want) < 0) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                }
+                __syncthreads();
+                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (!change && delta > 0 && tid == 0 && first >= lo && first < lo + cntn)
                     P.flow[in_arc] = (lower_state ? 0 : upper_in) + val;                // NS.cs:1018: stays a non-tree arc, at the other bound
                 int bad = 0;
@@ -759,35 +867,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
                 // ---- every node: re-label in[] in closed form; re-hung subtree: new depth and pi += sigma (NS.cs:1185-1209)
                 if (change) {
-                    const int base = b < a ? b + 1 : b - s + 1;                         // new index of u_in: first child of v_in
-                    const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
-                    const long long sigma = piV - piU - (dir_new_up ? (long long)a_cost : -(long long)a_cost);   // NS.cs:1187-1188
-                    const int dshift = dp_vin + 1 - dp_uin;
-                    const int sh_lo = b < a ? b + 1 : a + s, sh_len = b < a ? a - b - 1 : b - a - s + 1, sh_by = b < a ? s : -s;
                     for (int j = tid; j < cntn; j += kTT) {
                         const int x = in_s[j];
-                        if ((unsigned)(x - a) < (unsigned)s) {
-                            int off, l = 0;
-                            if (ns == 1) off = x - a;
-                            else {
-                                int r = ns - 1, l_in, l_z;                              // smallest l with x inside subtree(stem l)
-                                while (l < r) { const int mid = (l + r) >> 1; stem_io(mid, l_in, l_z); if ((unsigned)(x - l_in) < (unsigned)l_z) r = mid; else l = mid + 1; }
-                                stem_io(l, l_in, l_z);
-                                if (l == 0) off = x - l_in;
-                                else {
-                                    int p_in, p_z; stem_io(l - 1, p_in, p_z);
-                                    int rr = x - l_in;
-                                    if (x > p_in) rr -= p_z;
-                                    off = p_z + rr;
-                                }
-                            }
-                            const int nx = base + off, nd = dp_s[j] + dshift + 2 * l;
+                        int nx, nd;
+                        if (relabel(U, x, dp_s[j], nx, nd)) {
                             in_s[j] = nx; dp_s[j] = nd;
-                            atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)sigma);
+                            atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)U.sigma);
                             *reinterpret_cast<int2*>(&P.node[lo + j].in) = make_int2(nx, nd);
-                        } else if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {
-                            in_s[j] = x + sh_by; P.node[lo + j].in = x + sh_by;
-                        }
+                        } else if (nx != x) { in_s[j] = nx; P.node[lo + j].in = nx; }
                     }
                 }
                 if (bad) P.ctl->needs_wide = 1;
@@ -857,7 +944,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
-constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (8 + 4 * 4);
+constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (3 * 8 + 8 * 4);
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 

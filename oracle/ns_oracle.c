@@ -596,6 +596,15 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
     res->pivot_kind = kind;
     if (kind == 2 || kind == 3) res->initial_block_size = s->block_size;
 
+    if (opt->resume) {                                                        /* continue a solve this code checkpointed */
+        const ns_oracle_state *r = opt->resume;
+        size_t AA = (size_t)m + 2 * (size_t)n;
+        memcpy(s->parent, r->parent, N1 * 4); memcpy(s->pred, r->pred, N1 * 4); memcpy(s->thread, r->thread, N1 * 4);
+        memcpy(s->rev_thread, r->rev_thread, N1 * 4); memcpy(s->succ_num, r->succ_num, N1 * 4); memcpy(s->last_succ, r->last_succ, N1 * 4);
+        memcpy(s->pred_dir, r->pred_dir, N1); memcpy(s->state, r->state, AA); memcpy(s->flow, r->flow, AA * 8); memcpy(s->pi, r->pi, N1 * 8);
+        iterations = (int)r->iterations; s->next_arc = r->next_arc; s->block_size = r->block_size;
+        s->consecutive_low = r->consecutive_low; s->consecutive_high = r->consecutive_high;
+    }
     int64_t max_iterations = (int64_t)n * m; if (max_iterations < 1000000) max_iterations = 1000000;  /* NS.cs:280 */
     double t_price = 0, t_tree = 0, t_pot = 0;
     const int timing = opt->collect_phase_times;
@@ -639,6 +648,15 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
     if (kind == 2 || kind == 3) res->final_block_size = s->block_size;
     res->pricing_seconds = t_price; res->tree_seconds = t_tree; res->potential_seconds = t_pot;
 
+    if (res->stopped_early && opt->save) {
+        ns_oracle_state *w = opt->save;
+        size_t AA = (size_t)m + 2 * (size_t)n;
+        memcpy(w->parent, s->parent, N1 * 4); memcpy(w->pred, s->pred, N1 * 4); memcpy(w->thread, s->thread, N1 * 4);
+        memcpy(w->rev_thread, s->rev_thread, N1 * 4); memcpy(w->succ_num, s->succ_num, N1 * 4); memcpy(w->last_succ, s->last_succ, N1 * 4);
+        memcpy(w->pred_dir, s->pred_dir, N1); memcpy(w->state, s->state, AA); memcpy(w->flow, s->flow, AA * 8); memcpy(w->pi, s->pi, N1 * 8);
+        w->iterations = iterations; w->next_arc = s->next_arc; w->block_size = s->block_size;
+        w->consecutive_low = s->consecutive_low; w->consecutive_high = s->consecutive_high;
+    }
     if (res->stopped_early) { status = NS_STATUS_NOT_SOLVED; }
     else if (check_feasibility(s)) {
         status = NS_STATUS_OPTIMAL;

@@ -34,6 +34,16 @@ typedef struct {                 /* ProblemCharacteristics.cs */
     int64_t cost_range, capacity_range, total_supply, max_absolute_supply;
 } ns_oracle_characteristics;
 
+/* Solver state at a pivot boundary (test infrastructure: lets the CPU baseline time a window in the MIDDLE of a long solve
+ * by resuming from a checkpoint this same code wrote).  All arrays are caller-owned: [n+1] node arrays, [m+2n] arc arrays. */
+typedef struct {
+    int32_t *parent, *pred, *thread, *rev_thread, *succ_num, *last_succ;
+    int8_t *pred_dir, *state;
+    int64_t *flow, *pi;
+    int64_t iterations;
+    int32_t next_arc, block_size, consecutive_low, consecutive_high;
+} ns_oracle_state;
+
 typedef struct {
     int32_t supply_type;         /* NS_SUPPLY_*  (NS.cs:38 default Geq) */
     int32_t pivot_rule;          /* NS_PIVOT_*   (NS.cs:77 default BlockSearch) */
@@ -46,6 +56,8 @@ typedef struct {
     int32_t *trace_in_arc;       /* entering arc per pivot */
     int32_t *trace_u_out;        /* leaving node per pivot, -1 when the entering arc only flips bound */
     ns_oracle_config config;     /* used when auto_config == 0 (SetOptimizationConfig, NS.cs:557-561) */
+    const ns_oracle_state *resume; /* not NULL: continue from this state (its iterations count on; max_pivots is absolute) */
+    ns_oracle_state *save;       /* not NULL: filled with the state when the loop stops at max_pivots */
 } ns_oracle_options;
 
 typedef struct {

@@ -36,11 +36,64 @@ class Characteristics(C.Structure):
                [(k, C.c_int64) for k in ("cost_range", "capacity_range", "total_supply", "max_absolute_supply")]
 
 
+class CState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("parent", "pred", "thread", "rev_thread", "succ_num", "last_succ", "pred_dir", "state", "flow", "pi")] + \
+               [("iterations", C.c_int64), ("next_arc", C.c_int32), ("block_size", C.c_int32), ("consecutive_low", C.c_int32),
+                ("consecutive_high", C.c_int32)]
+
+
+class State:
+    """Solver state at a pivot boundary (checkpoint / resume of the CPU oracle; see ns_oracle.h)."""
+    NODE_I32 = ("parent", "pred", "thread", "rev_thread", "succ_num", "last_succ")
+
+    def __init__(self, n, m):
+        self.n, self.m = n, m
+        for k in self.NODE_I32:
+            setattr(self, k, np.zeros(n + 1, np.int32))
+        self.pred_dir = np.zeros(n + 1, np.int8); self.state = np.zeros(m + 2 * n, np.int8)
+        self.flow = np.zeros(m + 2 * n, np.int64); self.pi = np.zeros(n + 1, np.int64)
+        self.iterations = 0; self.next_arc = 0; self.block_size = 0; self.consecutive_low = 0; self.consecutive_high = 0
+
+    def c(self) -> CState:
+        c = CState()
+        for k in self.NODE_I32 + ("pred_dir", "state", "flow", "pi"):
+            setattr(c, k, getattr(self, k).ctypes.data)
+        c.iterations, c.next_arc, c.block_size = self.iterations, self.next_arc, self.block_size
+        c.consecutive_low, c.consecutive_high = self.consecutive_low, self.consecutive_high
+        return c
+
+    def take(self, c: CState):
+        self.iterations, self.next_arc, self.block_size = c.iterations, c.next_arc, c.block_size
+        self.consecutive_low, self.consecutive_high = c.consecutive_low, c.consecutive_high
+
+    def save(self, path):
+        """Compact file: rev_thread is derived, state / flow are stored sparse (most arcs sit at the lower bound with zero flow)."""
+        nz = np.nonzero(self.flow)[0].astype(np.int32)
+        ns = np.nonzero(self.state != 1)[0].astype(np.int32)
+        np.savez_compressed(path, n=self.n, m=self.m, parent=self.parent, pred=self.pred, thread=self.thread, succ_num=self.succ_num,
+                            last_succ=self.last_succ, pred_dir=self.pred_dir, pi=self.pi, flow_idx=nz, flow_val=self.flow[nz],
+                            state_idx=ns, state_val=self.state[ns],
+                            scalars=np.array([self.iterations, self.next_arc, self.block_size, self.consecutive_low, self.consecutive_high], np.int64))
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        st = cls(int(z["n"]), int(z["m"]))
+        for k in ("parent", "pred", "thread", "succ_num", "last_succ", "pred_dir", "pi"):
+            getattr(st, k)[:] = z[k]
+        st.rev_thread[st.thread] = np.arange(st.n + 1, dtype=np.int32)
+        st.state[:] = 1; st.state[z["state_idx"]] = z["state_val"]
+        st.flow[z["flow_idx"]] = z["flow_val"]
+        st.iterations, st.next_arc, st.block_size, st.consecutive_low, st.consecutive_high = (int(x) for x in z["scalars"])
+        return st
+
+
 class Options(C.Structure):
     _fields_ = [("supply_type", C.c_int32), ("pivot_rule", C.c_int32), ("optimized_pivot", C.c_int32),
                 ("auto_config", C.c_int32), ("simd_width", C.c_int32), ("collect_phase_times", C.c_int32),
                 ("max_pivots", C.c_int64), ("trace_capacity", C.c_int64),
-                ("trace_in_arc", C.c_void_p), ("trace_u_out", C.c_void_p), ("config", Config)]
+                ("trace_in_arc", C.c_void_p), ("trace_u_out", C.c_void_p), ("config", Config),
+                ("resume", C.c_void_p), ("save", C.c_void_p)]
 
 
 class Result(C.Structure):
@@ -107,7 +160,8 @@ def select_config(ch: Characteristics) -> Config:
 
 
 def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config: Config | None = None,
-          optimized_pivot=False, simd_width=4, max_pivots=0, trace=0, phase_times=False):
+          optimized_pivot=False, simd_width=4, max_pivots=0, trace=0, phase_times=False, resume: State | None = None,
+          save: State | None = None):
     """Returns (Result, flow[int64 m], pi[int64 n], trace_in_arc | None, trace_u_out | None)."""
     src, tgt, lo, up, co, su = _arrs(p)
     o = Options()
@@ -119,10 +173,17 @@ def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config:
     if trace:
         tin = np.full(trace, -2, np.int32); tout = np.full(trace, -2, np.int32)
         o.trace_capacity = trace; o.trace_in_arc = tin.ctypes.data; o.trace_u_out = tout.ctypes.data
+    c_res = c_save = None
+    if resume is not None:
+        c_res = resume.c(); o.resume = C.addressof(c_res)
+    if save is not None:
+        c_save = save.c(); o.save = C.addressof(c_save)
     res = Result()
     flow = np.zeros(p.m, np.int64); pi = np.zeros(p.n, np.int64)
     lib().ns_oracle_solve(C.c_int(p.n), C.c_int(p.m), _p(src), _p(tgt), _p(lo), _p(up), _p(co), _p(su),
                           C.byref(o), C.byref(res), _p(flow), _p(pi))
+    if save is not None and res.stopped_early:
+        save.take(c_save)
     return res, flow, pi, tin, tout
 
 
