@@ -128,6 +128,50 @@ __device__ __forceinline__ void publish_candidate(const Params& P, int buf, long
     P.part[(size_t)buf * gridDim.x + blockIdx.x] = r;
 }
 
+// Best Eligible inner loop (NS.cs:1649-1658) over quads of arcs: 128-bit loads of source / target / cost / state, the
+// two potential gathers, strict '<' in ascending arc order.  Software-pipelined: the next quad's arc data is in flight
+// while the current quad's potentials are gathered (the loop is latency-, not bandwidth-bound otherwise).
+struct ArcQuad { int4 s, t, c, st; };
+__device__ __forceinline__ ArcQuad load_quad(const Params& P, int q)
+{
+    ArcQuad a;
+    a.s = __ldg(reinterpret_cast<const int4*>(P.src) + q); a.t = __ldg(reinterpret_cast<const int4*>(P.tgt) + q);
+    a.c = __ldg(reinterpret_cast<const int4*>(P.cost) + q); a.st = __ldcg(reinterpret_cast<const int4*>(P.state) + q);
+    return a;
+}
+__device__ __forceinline__ void price_quad(const Params& P, const ArcQuad& a, int q, Key& best)
+{
+    // arc lists are usually grouped by tail node: consecutive arcs share pi[source], one gather serves the run
+    const long long pt0 = __ldcg(P.pi + a.t.x), pt1 = __ldcg(P.pi + a.t.y), pt2 = __ldcg(P.pi + a.t.z), pt3 = __ldcg(P.pi + a.t.w);
+    const long long ps0 = __ldcg(P.pi + a.s.x);
+    const long long ps1 = a.s.y == a.s.x ? ps0 : __ldcg(P.pi + a.s.y);
+    const long long ps2 = a.s.z == a.s.y ? ps1 : __ldcg(P.pi + a.s.z);
+    const long long ps3 = a.s.w == a.s.z ? ps2 : __ldcg(P.pi + a.s.w);
+    const long long r0 = (long long)a.st.x * ((long long)a.c.x + ps0 - pt0);
+    const long long r1 = (long long)a.st.y * ((long long)a.c.y + ps1 - pt1);
+    const long long r2 = (long long)a.st.z * ((long long)a.c.z + ps2 - pt2);
+    const long long r3 = (long long)a.st.w * ((long long)a.c.w + ps3 - pt3);
+    const int e = q << 2;
+    if (r0 < best.a) { best.a = r0; best.b = e; }
+    if (r1 < best.a) { best.a = r1; best.b = e + 1; }
+    if (r2 < best.a) { best.a = r2; best.b = e + 2; }
+    if (r3 < best.a) { best.a = r3; best.b = e + 3; }
+}
+__device__ __forceinline__ void sweep_quads(const Params& P, int first, int stride, int nquad, Key& best)
+{
+    int q = first;
+    if (q >= nquad) return;
+    ArcQuad cur = load_quad(P, q);
+    for (;;) {
+        const int qn = q + stride;
+        ArcQuad nxt = cur;
+        if (qn < nquad) nxt = load_quad(P, qn);
+        price_quad(P, cur, q, best);
+        if (qn >= nquad) break;
+        cur = nxt; q = qn;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 
 __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
@@ -290,24 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
         } else {  // PK_BEST: coalesced 128-bit sweep over all S arcs, lowest arc id wins ties (NS.cs:1649-1658)
             Key best; best.a = 0; best.b = INT_MAX; best.idx = -1;
             const int nquad = S >> 2;
-            const int4* src4 = reinterpret_cast<const int4*>(P.src);
-            const int4* tgt4 = reinterpret_cast<const int4*>(P.tgt);
-            const int4* cost4 = reinterpret_cast<const int4*>(P.cost);
-            const int4* st4 = reinterpret_cast<const int4*>(P.state);
-            for (int q = cta * kThreads + tid; q < nquad; q += G * kThreads) {
-                const int4 s = __ldg(src4 + q), t = __ldg(tgt4 + q), c = __ldg(cost4 + q), st = __ldcg(st4 + q);
-                const long long ps0 = __ldcg(P.pi + s.x), ps1 = __ldcg(P.pi + s.y), ps2 = __ldcg(P.pi + s.z), ps3 = __ldcg(P.pi + s.w);
-                const long long pt0 = __ldcg(P.pi + t.x), pt1 = __ldcg(P.pi + t.y), pt2 = __ldcg(P.pi + t.z), pt3 = __ldcg(P.pi + t.w);
-                const long long r0 = (long long)st.x * ((long long)c.x + ps0 - pt0);
-                const long long r1 = (long long)st.y * ((long long)c.y + ps1 - pt1);
-                const long long r2 = (long long)st.z * ((long long)c.z + ps2 - pt2);
-                const long long r3 = (long long)st.w * ((long long)c.w + ps3 - pt3);
-                const int e = q << 2;
-                if (r0 < best.a) { best.a = r0; best.b = e; }
-                if (r1 < best.a) { best.a = r1; best.b = e + 1; }
-                if (r2 < best.a) { best.a = r2; best.b = e + 2; }
-                if (r3 < best.a) { best.a = r3; best.b = e + 3; }
-            }
+            sweep_quads(P, cta * kThreads + tid, G * kThreads, nquad, best);
             for (int e = (nquad << 2) + cta * kThreads + tid; e < S; e += G * kThreads) {
                 const long long r = reduced_cost(P, e);
                 if (r < best.a) { best.a = r; best.b = e; }
@@ -555,24 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_price_sweep_kernel(const Param
     const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x, S = P.S;
     Key best; best.a = 0; best.b = INT_MAX; best.idx = -1;
     const int nquad = S >> 2;
-    const int4* src4 = reinterpret_cast<const int4*>(P.src);
-    const int4* tgt4 = reinterpret_cast<const int4*>(P.tgt);
-    const int4* cost4 = reinterpret_cast<const int4*>(P.cost);
-    const int4* st4 = reinterpret_cast<const int4*>(P.state);
-    for (int q = cta * kThreads + tid; q < nquad; q += G * kThreads) {
-        const int4 s = __ldg(src4 + q), t = __ldg(tgt4 + q), c = __ldg(cost4 + q), st = __ldcg(st4 + q);
-        const long long ps0 = __ldcg(P.pi + s.x), ps1 = __ldcg(P.pi + s.y), ps2 = __ldcg(P.pi + s.z), ps3 = __ldcg(P.pi + s.w);
-        const long long pt0 = __ldcg(P.pi + t.x), pt1 = __ldcg(P.pi + t.y), pt2 = __ldcg(P.pi + t.z), pt3 = __ldcg(P.pi + t.w);
-        const long long r0 = (long long)st.x * ((long long)c.x + ps0 - pt0);
-        const long long r1 = (long long)st.y * ((long long)c.y + ps1 - pt1);
-        const long long r2 = (long long)st.z * ((long long)c.z + ps2 - pt2);
-        const long long r3 = (long long)st.w * ((long long)c.w + ps3 - pt3);
-        const int e = q << 2;
-        if (r0 < best.a) { best.a = r0; best.b = e; }
-        if (r1 < best.a) { best.a = r1; best.b = e + 1; }
-        if (r2 < best.a) { best.a = r2; best.b = e + 2; }
-        if (r3 < best.a) { best.a = r3; best.b = e + 3; }
-    }
+    sweep_quads(P, cta * kThreads + tid, G * kThreads, nquad, best);
     for (int e = (nquad << 2) + cta * kThreads + tid; e < S; e += G * kThreads) {
         const long long r = reduced_cost(P, e);
         if (r < best.a) { best.a = r; best.b = e; }

@@ -111,7 +111,6 @@ struct Pending {                    // one pivot's update in closed form: what t
 
 struct TeamShared {
     Book bk;
-    Pending pend;
     Cand cl[kCandCap];              // cycle-node candidates of this slice (owner scan)
     Cand wc[2][kTW];                // per-warp winners (hop 2 gather, owner slow path)
     PWin pw[kTW];                   // per-warp pricing winners
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
         }
-        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; sh.pend.valid = 0; }
+        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; }
         if (__syncthreads_or(bad)) { if (tid == 0) P.ctl->needs_wide = 1; }
     }
     if (tid == 0) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
@@ -273,6 +272,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         return idx == patch_arc0 ? patch_st0 : idx == patch_arc1 ? patch_st1 : idx == patch2_arc0 ? patch2_st0 : idx == patch2_arc1 ? patch2_st1 : st;
     };
     long long iterations = 0;
+    Pending Uprev;                                       // the previous pivot's update (every thread computes it; see `replay`)
+    Uprev.valid = Uprev.change = Uprev.a = Uprev.s = Uprev.b = Uprev.longstem = Uprev.dshift = Uprev.par = Uprev.seq = 0; Uprev.ns = 1; Uprev.sigma = 0;
 #define PROBE(i) do { if (tid == 0 && ((i) < 8 ? cta == 0 : cta == NP)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
 #define TICK(acc) do { if (cta == 0 && tid == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     pf_next = next_arc; pf_B = B; pf_upto = k - 1;
                 }
                 const bool replay = pf_upto < k - 1;                     // exactly update k-1 is missing from the staged records
-                const Pending U = sh.pend;
+                const Pending U = Uprev;
                 int bq = -1;
 #pragma unroll
                 for (int j = 0; j < kPf; ++j) {
@@ -690,6 +691,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (tid == 0) sh.cnt = 0;
             __syncthreads();
             const int nw = (nown + 31) >> 5;                                            // warps that poll
+            if (!pricer && warp == kTW - 1 && lane < NP) {
+                // owners: update k may touch the mirror only after every pricer has gathered the next block's node records
+                // (GATHERED(k+1)); polled here, next to the CYC records, so that it costs nothing when it is already there
+                const unsigned want = (unsigned)(k + 1);
+                const unsigned* p = P.done + (size_t)(G + lane) * 32;
+                unsigned spins = 0; long long t0 = 0;
+                while ((int)(ld_vol_u32(p) - want) < 0) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+            }
             if (warp < nw) {
                 Cand b1 = cand_none(), b2 = cand_none();
                 int c = 0;
@@ -805,19 +814,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (tid == 0) {
                     P.state[patch_arc0] = patch_st0;
                     if (patch_arc1 >= 0) P.state[patch_arc1] = patch_st1;
-                    sh.pend = U;                                                        // replayed by the next pricing (see above)
                 }
-                __syncthreads();
+                Uprev = U;                                                              // replayed by the next pricing (see above)
             } else {
-                // update k may touch the mirror only after every pricer has gathered the next block's node records
-                if (tid < NP) {
-                    const unsigned want = (unsigned)(k + 1);
-                    const unsigned* p = P.done + (size_t)(G + tid) * 32;
-                    unsigned spins = 0; long long t0 = 0;
-                    while ((int)(ld_vol_u32(p) - want) < 0) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                }
-                __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (!change && delta > 0 && tid == 0 && first >= lo && first < lo + cntn)
                     P.flow[in_arc] = (lower_state ? 0 : upper_in) + val;                // NS.cs:1018: stays a non-tree arc, at the other bound
                 int bad = 0;

@@ -28,10 +28,12 @@ def _oracle_cfg(cfg: mcf.OptimizationConfig):
     return c
 
 
-def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, optimized=False, expect_cost=None):
+def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, optimized=False, expect_cost=None, engine=None):
     """Solve on the GPU and on the oracle; everything observable must be identical."""
     ns = mcf.NetworkSimplex.from_problem(p)
     ns.SetPivotRule(rule).SetSupplyType(supply_type)
+    if engine is not None:
+        ns.set_engine_options(engine=engine)
     if cfg is not None:
         ns.SetOptimizationConfig(cfg)
     if optimized:
@@ -208,6 +210,37 @@ def test_grid_time_expanded_small():
     """BASELINE.json config 4 at 64x64 and 128x96: long, thin time-expanded grid (deep trees, long cycles)."""
     check_parity(instances.grid_time_expanded(64, 64), cfg=mcf.OptimizationConfig())
     check_parity(instances.grid_time_expanded(128, 96, seed=7), cfg=mcf.OptimizationConfig())
+
+
+def test_both_engines_and_both_flow_widths():
+    """Block Search runs on the team engine (int32 or int64 resident flows) or on the flat engine; all three must agree with
+    the oracle.  Wide mode is entered (a) up front when a finite capacity does not fit 31 bits, (b) by a re-run when a flow
+    leaves the int32 range during a narrow solve."""
+    p = instances.netgen8(12)
+    for eng in ("team", "flat"):
+        ns, _ = check_parity(p, cfg=mcf.OptimizationConfig(), engine=eng)
+        assert ns.GetMetrics().engine == (2 if eng == "team" else 1)
+    assert check_parity(p, cfg=mcf.OptimizationConfig(), engine="team")[0].GetMetrics().wide_flows == 0
+    big = Problem(p.n, p.m, p.source, p.target, p.lower, p.upper * 5_000_000, p.cost, p.supply * 5_000_000, "netgen12_big_caps")
+    ns, _ = check_parity(big, cfg=mcf.OptimizationConfig(), engine="team")          # (a) capacities up to 5e9
+    assert ns.GetMetrics().wide_flows == 1
+    inf = Problem(p.n, p.m, p.source, p.target, p.lower, np.full(p.m, instances.INF, np.int64), p.cost, p.supply * 5_000_000, "netgen12_uncapacitated")
+    ns, _ = check_parity(inf, cfg=mcf.OptimizationConfig(), engine="team")          # (b) supplies of 5e9 per source on uncapacitated arcs
+    assert ns.GetMetrics().wide_flows == 1
+
+
+def test_team_engine_multi_block_searches_and_adaptive_blocks(load_fixture):
+    """Searches that run past the first block (pricer-per-block rounds, the late ENTER record), the final full sweep, and the
+    adaptive block size changing under the staged pricing pipeline."""
+    p = load_fixture("circulation_1000_0_05")
+    cfg = mcf.OptimizationConfig(Flags=mcf.OptimizationFlags.AdaptiveBlockSize | mcf.OptimizationFlags.SmallBlocksForDense)
+    for pricers in (1, 3):
+        ns = mcf.NetworkSimplex.from_problem(p)
+        ns.SetOptimizationConfig(cfg)
+        ns.set_engine_options(engine="team", lookahead_blocks=pricers)
+        assert ns.Solve() == mcf.SolverStatus.Optimal
+        M = ns.GetMetrics()
+        assert (M.iterations, M.initial_block_size, M.final_block_size, M.pricer_ctas) == (144041, 50, 28, pricers)
 
 
 def _large(name):

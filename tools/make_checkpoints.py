@@ -17,12 +17,16 @@ os.makedirs(out_dir, exist_ok=True)
 cfg = oracle.default_config()
 st = None
 for i, f in enumerate(fr):
+    path = os.path.join(out_dir, f"ckpt_{p.name}_{i}.npz")
+    if os.path.exists(path) and "--redo" not in sys.argv:          # continue from what is already there
+        st = oracle.State.load(path)
+        print(f"checkpoint {i}: present (pivot {st.iterations})", flush=True)
+        continue
     target = int(total * f)
     nxt = oracle.State(p.n, p.m)
     t = time.time()
     r, *_ = oracle.solve(p, config=cfg, max_pivots=target, resume=st, save=nxt)
     assert r.stopped_early and nxt.iterations == target, (r.iterations, target)
-    path = os.path.join(out_dir, f"ckpt_{p.name}_{i}.npz")
     nxt.save(path)
     print(f"checkpoint {i}: pivot {target} of {total}, {time.time() - t:.1f} s, {os.path.getsize(path) / 1e6:.1f} MB -> {path}", flush=True)
     st = nxt
