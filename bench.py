@@ -63,6 +63,11 @@ def cpu_sample(p, k, prefix):
         start = st.iterations
         r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + MID_WINDOW[k], resume=st)
         wins.append({"from_pivot": int(start), "pivots": int(r.iterations - start), "seconds": r.loop_seconds})
+    # the reference itself zero-fills a stackalloc int[n] on every stem re-hang (NetworkSimplex.cs:1085); the port hoists that
+    # scratch (conservative).  One mid-solve window is repeated with the zero-fill, for the record only.
+    st = oracle.State.load(ck[len(ck) // 2]); start = st.iterations
+    r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + MID_WINDOW[k] // 4, resume=st, emulate_stackalloc=True)
+    wins[1 + len(ck) // 2]["us_per_pivot_with_reference_stackalloc"] = 1e6 * r.loop_seconds / max(r.iterations - start, 1)
     # each window stands for the stretch of the solve up to the next window's start
     starts = [w["from_pivot"] for w in wins] + [total]
     est_seconds = sum(w["seconds"] / w["pivots"] * (starts[i + 1] - starts[i]) for i, w in enumerate(wins))

@@ -28,6 +28,7 @@ extern "C" size_t mcfk_team_smem_bytes(int slice, int wide);
 extern "C" int mcfk_team_max_slice(int device, int wide);
 extern "C" int mcfk_team_max_ctas(int device, int slice, int wide);
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream);
+extern "C" void mcfk_team_replicas(int* ent, int* cyc);
 
 namespace {
 
@@ -345,9 +346,12 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
     CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
     CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)(team + pricers) * 32));     // DONE flags of the owners + GATHERED flags of the pricers
-    const size_t w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords, w_cyc = (size_t)2 * team * mcf::kMailWords;
+    int rep_ent = 1, rep_cyc = 1;
+    mcfk_team_replicas(&rep_ent, &rep_cyc);
+    const size_t w_ent = (size_t)2 * rep_ent * pricers * mcf::kMailWords, w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords;
+    const size_t w_cyc = (size_t)2 * rep_cyc * team * mcf::kMailWords, w_hdr = (size_t)2 * team * mcf::kMailWords;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
-    const size_t seg_off = (2 * w_pr + w_late + 2 * w_cyc + 7) & ~(size_t)7;
+    const size_t seg_off = (w_ent + w_pr + w_late + w_cyc + w_hdr + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
     for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = u == n ? 0 : 1; }
@@ -367,7 +371,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     P->n = n; P->m = m; P->S = S; P->A = A;
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
     P->node = h->d_node.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
-    P->ent0 = h->d_mail.p; P->prc = h->d_mail.p + w_pr; P->late = h->d_mail.p + 2 * w_pr; P->cyc = h->d_mail.p + 2 * w_pr + w_late;
+    P->ent0 = h->d_mail.p; P->prc = P->ent0 + w_ent; P->late = P->prc + w_pr; P->cyc = P->late + w_late;
     P->stemhdr = P->cyc + w_cyc; P->stemseg = h->d_mail.p + seg_off;
     P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
     return MCF_OK;

@@ -35,6 +35,8 @@ namespace {
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
 constexpr int kPf = 4;                                  // arcs per pricer thread staged ahead (2048 per pricing CTA)
+constexpr int kRepEnt = 4;                              // replicas of every ENTER record: a reader polls replica (cta % kRepEnt)
+constexpr int kRepCyc = 6;                              // replicas of every CYC record (fewer pollers per line, profiles/r01_micro_hop.txt)
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
 __device__ __forceinline__ int4 ld_vol4(const int4* p)
@@ -60,6 +62,16 @@ __device__ __forceinline__ unsigned long long gtimer()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// asynchronous global -> shared copies (LDGSTS): immutable arc data streams from DRAM without holding registers
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ int lo32(long long v) { return (int)(unsigned)(unsigned long long)v; }
 __device__ __forceinline__ int hi32(long long v) { return (int)(unsigned)((unsigned long long)v >> 32); }
 __device__ __forceinline__ long long mk64(int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
@@ -123,6 +135,9 @@ struct TeamShared {
 // time-out / abort check for spin loops; true = give up
 __device__ __forceinline__ bool spin_check(unsigned& spins, long long& t0, const TeamParams& P)
 {
+#ifdef MCF_SPIN_SLEEP
+    __nanosleep(MCF_SPIN_SLEEP);                        // back off: fewer polling requests in flight at L2
+#endif
     if ((++spins & 255u) != 0) return false;
     if (t0 == 0) { t0 = clock64(); return false; }
     if (*(volatile int*)&P.ctl->abort) return true;
@@ -255,6 +270,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
         }
+        if (!pricer) for (int j = cntn + tid; j < P.slice; j += kTT) { in_s[j] = 0; sz_s[j] = 0; dp_s[j] = 0; pd_s[j] = -2; fl_s[j] = 0; up_s[j] = 0; }   // padding: on no cycle, never relabelled
         if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; }
         if (__syncthreads_or(bad)) { if (tid == 0) P.ctl->needs_wide = 1; }
     }
@@ -265,6 +281,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int pf_next = -1, pf_B = 0;                          // what is staged: this pricer's share of block [pf_next, pf_next + pf_B)
     long long pf_upto = 0;                               // ... as of "all updates of pivots <= pf_upto applied"
     long long done_seen = 0;                             // DONE(j) observed from every owner for all j <= done_seen
+    int spec_cursor = -1, spec_B = 0;                    // arc data of block [spec_cursor, +spec_B) is in flight into the staging area
+    int stv[kPf];                                        // ... with its arc states here (see stage_static_begin)
+#pragma unroll
+    for (int j = 0; j < kPf; ++j) stv[j] = 0;
     // arc-state changes of the last two pivots: applied on top of whatever a scan reads (staged or global), newest first, so a
     // scan never depends on how fast this CTA's own state[] stores become visible to its other warps
     int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0, patch2_arc0 = -1, patch2_st0 = 0, patch2_arc1 = -1, patch2_st1 = 0;
@@ -308,6 +328,26 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 pf_st[q] = __ldcg(P.state + idx); pf_up[q] = __ldg(P.upper + idx);
             }
         }
+    };
+    // the same, asynchronously: src / tgt / cost / capacity are immutable and go global -> shared with cp.async; `state` is
+    // mutable, so it is read around L1 into `stv` and stored by stage_static_finish()
+    auto stage_static_begin = [&](int cursor, int s_lo, int s_hi, int (&stv)[kPf]) {
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) {
+            const int q = tid + j * kTT, off = s_lo + q;
+            stv[j] = 0;
+            if (off < s_hi) {
+                int idx = cursor + off; if (idx >= S) idx -= S;
+                cp_async4(pf_src + q, P.src + idx); cp_async4(pf_tgt + q, P.tgt + idx); cp_async4(pf_cost + q, P.cost + idx);
+                cp_async8(pf_up + q, P.upper + idx);
+                stv[j] = __ldcg(P.state + idx);
+            }
+        }
+    };
+    auto stage_static_finish = [&](int s_lo, int s_hi, const int (&stv)[kPf]) {
+        cp_async_wait_all();
+#pragma unroll
+        for (int j = 0; j < kPf; ++j) { const int q = tid + j * kTT; if (s_lo + q < s_hi) pf_st[q] = stv[j]; }
     };
     // gather both ends' node records {pi, in, depth} of the staged share from the mirror
     auto stage_gather = [&](int s_lo, int s_hi) {
@@ -441,7 +481,17 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
                 PWin mine = pwin_none();
                 if (ww >= 0) mine = sh.pw[ww];
-                if (lane < 7) post_pwin(P.ent0 + ((size_t)par * NP + cta) * kMailWords, mine, 0, seq, lane);
+                if (lane < 7 * kRepEnt) post_pwin(P.ent0 + (((size_t)par * kRepEnt + lane / 7) * NP + cta) * kMailWords, mine, 0, seq, lane % 7);
+            }
+            // 98.5 % of the searches end in this first block: the next pivot's block then starts at its last arc (NS.cs:1397).
+            // Start streaming that block's arc data now, under the collect hop; it is re-done in the rare other case.
+            spec_cursor = -1;
+            if (fits) {
+                const int blk0 = B < S ? B : S;
+                int e = next_arc;
+                if (blk0 < S || (long long)S % B == 0) { e = next_arc + blk0 - 1; if (e >= S) e -= S; }
+                stage_static_begin(e, s_lo, s_hi, stv);                  // (every read of the staging area is behind the barrier above)
+                spec_cursor = e; spec_B = B;
             }
             PROBE(1);
         }
@@ -450,11 +500,17 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (tid < NP * 7) {
             const int p = tid / 7, w = tid - p * 7;
             int4 v;
-            if (!poll_word(P.ent0 + ((size_t)par * NP + p) * kMailWords + w, seq, v, P)) sh.abort = 1;
+            if (!poll_word(P.ent0 + (((size_t)par * kRepEnt + cta % kRepEnt) * NP + p) * kMailWords + w, seq, v, P)) sh.abort = 1;
             sh.rec[p][w] = v;
         }
-        __syncthreads();
+        int done_ok = 1;
+        if (pricer && k > 1 && done_seen < k - 1 && tid >= 128 && tid < 128 + nown)
+            // pricers: one look at DONE(k-1) under the same hop - if every owner is through, the next block's node records can
+            // be gathered without another round trip (otherwise wait_done() below polls)
+            done_ok = (int)(ld_vol_u32(P.done + (size_t)(NP + tid - 128) * 32) - (unsigned)(k - 1)) >= 0;
+        done_ok = __syncthreads_and(done_ok);
         if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        if (pricer && k > 1 && done_seen < k - 1 && done_ok) done_seen = k - 1;
         {
             int bp = -1; long long brc = 0; int boff = INT_MAX;
             for (int p = 0; p < NP; ++p) {
@@ -585,9 +641,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // path) and BEFORE any owner applies update k: owners wait for GATHERED(k+1) below.  Update k is replayed at pricing.
             int s_lo, s_hi;
             const bool fits = share(B, s_lo, s_hi);
-            if (fits) stage_static(next_arc, s_lo, s_hi);
+            if (fits && !(spec_cursor == next_arc && spec_B == B)) {     // not what was predicted: drain and start over
+                cp_async_wait_all();
+                stage_static_begin(next_arc, s_lo, s_hi, stv);
+            }
+            spec_cursor = -1;
             if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            if (fits) { stage_gather(s_lo, s_hi); pf_next = next_arc; pf_B = B; pf_upto = k - 1; } else pf_next = -1;
+            if (fits) { stage_static_finish(s_lo, s_hi, stv); stage_gather(s_lo, s_hi); pf_next = next_arc; pf_B = B; pf_upto = k - 1; } else pf_next = -1;
             __syncthreads();
             if (tid == 0) st_vol_u32(P.done + (size_t)(G + cta) * 32, (unsigned)(k + 1));      // GATHERED(k+1)
             PROBE(3);
@@ -619,21 +679,28 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (!pricer) {
             if (tid == 0) sh.ncand = 0;
             __syncthreads();
-            for (int j = tid; j < cntn; j += kTT) {
-                const int in_u = in_s[j], sz_u = sz_s[j];
-                const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
-                const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
-                if (hasF != hasS) {
-                    const int slot = atomicAdd(&sh.ncand, 1);
-                    if (slot < kCandCap) sh.cl[slot] = make_cand(j, in_u, sz_u, hasF);
+            // four nodes per 128-bit shared-memory load; the slice is padded to a multiple of 8 with nodes that match nothing
+            const int nquad = cntn > 0 ? (cntn + 3) >> 2 : 0;
+            for (int q4 = tid; q4 < nquad; q4 += kTT) {
+                const int4 vi = reinterpret_cast<const int4*>(in_s)[q4], vz = reinterpret_cast<const int4*>(sz_s)[q4];
+                const int xi[4] = {vi.x, vi.y, vi.z, vi.w}, xz[4] = {vz.x, vz.y, vz.z, vz.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool hasF = (unsigned)(inF - xi[e]) < (unsigned)xz[e];
+                    const bool hasS = (unsigned)(inS - xi[e]) < (unsigned)xz[e];
+                    if (hasF != hasS) {
+                        const int slot = atomicAdd(&sh.ncand, 1);
+                        if (slot < kCandCap) sh.cl[slot] = make_cand(q4 * 4 + e, xi[e], xz[e], hasF);
+                    }
                 }
             }
             __syncthreads();
             nc = sh.ncand;
             PROBE(10);
-            int4* const rec = P.cyc + ((size_t)par * G + cta) * kMailWords;
+            // the record goes out in kRepCyc copies (lane l writes word l % 5 of copy l / 5)
+            int4* const rec = P.cyc + (((size_t)par * kRepCyc + lane / 5) * G + cta) * kMailWords;
             if (nc == 0) {
-                if (tid < 5) st_vol4(rec + tid, make_int4(0, 0, 0, seq));
+                if (tid < 5 * kRepCyc) st_vol4(rec + lane % 5, make_int4(0, 0, 0, seq));
             } else {
                 Cand m1 = cand_none(), m2 = cand_none();
                 if (nc <= kCandCap) {
@@ -673,14 +740,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         if (w2 >= 0) m2 = sh.wc[1][w2];
                     }
                 }
-                if (warp == 0 && lane < 5) {
+                if (warp == 0 && lane < 5 * kRepCyc) {
+                    const int wd = lane % 5;
                     int4 w;
-                    if (lane == 0) w = make_int4(nc, (m1.zero & 1) | ((m2.zero & 1) << 1) | (m1.pd >= 0 ? 4 : 0) | (m2.pd >= 0 ? 8 : 0), 0, seq);
-                    else if (lane == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
-                    else if (lane == 2) w = make_int4(m1.sz, m1.pd, m1.dp, seq);
-                    else if (lane == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
+                    if (wd == 0) w = make_int4(nc, (m1.zero & 1) | ((m2.zero & 1) << 1) | (m1.pd >= 0 ? 4 : 0) | (m2.pd >= 0 ? 8 : 0), 0, seq);
+                    else if (wd == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
+                    else if (wd == 2) w = make_int4(m1.sz, m1.pd, m1.dp, seq);
+                    else if (wd == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
                     else w = make_int4(m2.sz, m2.pd, m2.dp, seq);
-                    st_vol4(rec + lane, w);
+                    st_vol4(rec + wd, w);
                 }
             }
             PROBE(11);
@@ -704,7 +772,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 int c = 0;
                 if (tid < nown) {
                     int4 w[5];
-                    if (!poll_rec<5>(P.cyc + ((size_t)par * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
+                    if (!poll_rec<5>(P.cyc + (((size_t)par * kRepCyc + cta % kRepCyc) * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
                     else {
                         c = w[0].x;
                         if (w[0].y & 4) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.dp = w[2].z; b1.zero = w[0].y & 1; }
@@ -865,15 +933,27 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     __syncthreads();                                                    // the relabel pass below rewrites in_s
                 }
                 // ---- every node: re-label in[] in closed form; re-hung subtree: new depth and pi += sigma (NS.cs:1185-1209)
+                PROBE(15);
                 if (change) {
-                    for (int j = tid; j < cntn; j += kTT) {
-                        const int x = in_s[j];
-                        int nx, nd;
-                        if (relabel(U, x, dp_s[j], nx, nd)) {
-                            in_s[j] = nx; dp_s[j] = nd;
-                            atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)U.sigma);
-                            *reinterpret_cast<int2*>(&P.node[lo + j].in) = make_int2(nx, nd);
-                        } else if (nx != x) { in_s[j] = nx; P.node[lo + j].in = nx; }
+                    const int sh_lo = b < a ? b + 1 : a + s, sh_len = b < a ? a - b - 1 : b - a - s + 1, sh_by = b < a ? s : -s;
+                    // consecutive lanes <-> consecutive nodes (the mirror stores coalesce), four independent nodes per thread in flight
+                    for (int j0 = tid; j0 < cntn; j0 += 4 * kTT) {
+                        int xv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { const int j = j0 + e * kTT; xv[e] = j < cntn ? in_s[j] : 0; }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int x = xv[e], j = j0 + e * kTT;
+                            if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {                // between the old and the new place: shift
+                                in_s[j] = x + sh_by; P.node[lo + j].in = x + sh_by;
+                            } else if ((unsigned)(x - a) < (unsigned)s) {                  // re-hung subtree
+                                int nx, nd;
+                                relabel(U, x, dp_s[j], nx, nd);
+                                in_s[j] = nx; dp_s[j] = nd;
+                                atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)U.sigma);
+                                *reinterpret_cast<int2*>(&P.node[lo + j].in) = make_int2(nx, nd);
+                            }
+                        }
                     }
                 }
                 if (bad) P.ctl->needs_wide = 1;
@@ -975,6 +1055,8 @@ extern "C" int mcfk_team_max_ctas(int device, int slice, int wide)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, team_fn(wide), mcf::kTT, smem) != cudaSuccess) return -3;
     return per_sm * prop.multiProcessorCount;
 }
+
+extern "C" void mcfk_team_replicas(int* ent, int* cyc) { *ent = mcf::kRepEnt; *cyc = mcf::kRepCyc; }
 
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream)
 {

@@ -488,7 +488,9 @@ static void update_tree_structure(ns_t *s)
         int thread_continue = old_rev_thread == v_in ? thread[old_last_succ] : thread[v_in];
         int stem = u_in, par_stem = v_in, next_stem, last = last_succ[u_in], before, after = thread[last];
         thread[v_in] = u_in;
-        int *dirty = s->dirty_revs; dirty[0] = v_in; int dirty_count = 1;
+        int *dirty = s->dirty_revs;
+        if (s->opt->emulate_stackalloc) memset(dirty, 0, (size_t)s->n * sizeof(int));   /* NS.cs:1085: stackalloc is zero-initialised */
+        dirty[0] = v_in; int dirty_count = 1;
         while (stem != u_out) {
             next_stem = parent[stem];
             thread[last] = next_stem; dirty[dirty_count++] = last;

@@ -58,6 +58,10 @@ typedef struct {
     ns_oracle_config config;     /* used when auto_config == 0 (SetOptimizationConfig, NS.cs:557-561) */
     const ns_oracle_state *resume; /* not NULL: continue from this state (its iterations count on; max_pivots is absolute) */
     ns_oracle_state *save;       /* not NULL: filled with the state when the loop stops at max_pivots */
+    int32_t emulate_stackalloc;  /* 1: zero-fill an int[n] scratch on every stem re-hang like the reference's
+                                    `stackalloc int[_nodeCount]` (NS.cs:1085; no SkipLocalsInit) - timing fidelity only.
+                                    Default 0 = the scratch is hoisted (what a C/C++ port would do; conservative baseline). */
+    int32_t _pad2;
 } ns_oracle_options;
 
 typedef struct {

@@ -93,7 +93,7 @@ class Options(C.Structure):
                 ("auto_config", C.c_int32), ("simd_width", C.c_int32), ("collect_phase_times", C.c_int32),
                 ("max_pivots", C.c_int64), ("trace_capacity", C.c_int64),
                 ("trace_in_arc", C.c_void_p), ("trace_u_out", C.c_void_p), ("config", Config),
-                ("resume", C.c_void_p), ("save", C.c_void_p)]
+                ("resume", C.c_void_p), ("save", C.c_void_p), ("emulate_stackalloc", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -161,7 +161,7 @@ def select_config(ch: Characteristics) -> Config:
 
 def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config: Config | None = None,
           optimized_pivot=False, simd_width=4, max_pivots=0, trace=0, phase_times=False, resume: State | None = None,
-          save: State | None = None):
+          save: State | None = None, emulate_stackalloc=False):
     """Returns (Result, flow[int64 m], pi[int64 n], trace_in_arc | None, trace_u_out | None)."""
     src, tgt, lo, up, co, su = _arrs(p)
     o = Options()
@@ -173,6 +173,7 @@ def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config:
     if trace:
         tin = np.full(trace, -2, np.int32); tout = np.full(trace, -2, np.int32)
         o.trace_capacity = trace; o.trace_in_arc = tin.ctypes.data; o.trace_u_out = tout.ctypes.data
+    o.emulate_stackalloc = int(emulate_stackalloc)
     c_res = c_save = None
     if resume is not None:
         c_res = resume.c(); o.resume = C.addressof(c_res)
