@@ -511,18 +511,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         done_ok = __syncthreads_and(done_ok);
         if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
         if (pricer && k > 1 && done_seen < k - 1 && done_ok) done_seen = k - 1;
+        int win_rec = -1;                                 // round-0 record that holds the entering arc (every thread decodes it itself)
         {
-            int bp = -1; long long brc = 0; int boff = INT_MAX;
-            for (int p = 0; p < NP; ++p) {
-                if (sh.rec[p][0].x < 0) continue;
-                const long long rc = mk64(sh.rec[p][5].x, sh.rec[p][5].y); const int off = sh.rec[p][4].z;
-                if (bp < 0 || rc < brc || (rc == brc && off < boff)) { bp = p; brc = rc; boff = off; }
-            }
-            if (bp >= 0) {
-                if (tid == 0) sh.win = unpack_pwin(sh.rec[bp]);
-                have_win = true;
-                search_end = B < S ? B : S;
-            }
+            // arg-min of (reduced cost, scan offset) over the pricers' records, redundantly in every warp
+            const bool v = lane < NP && sh.rec[lane < NP ? lane : 0][0].x >= 0;
+            const int pl = lane < NP ? lane : 0;
+            win_rec = warp_argmin(v, mk64(sh.rec[pl][5].x, sh.rec[pl][5].y), sh.rec[pl][4].z);
+            if (win_rec >= 0) { have_win = true; search_end = B < S ? B : S; }
         }
         if (!have_win) {
             if (pricer) {
@@ -605,8 +600,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 have_win = sh.rec[0][0].x >= 0;
                 if (have_win && tid == 0) sh.win = unpack_pwin(sh.rec[0]);
             }
+            __syncthreads();
         }
-        __syncthreads();
         if (pricer) {
             // NS.cs:1397-1438: cursor, counters, adaptive block size - every pricer keeps the same copy
             if (tid == 0) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
@@ -653,7 +648,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             PROBE(3);
         } else PROBE(9);
 
-        const PWin ent = sh.win;
+        const PWin ent = win_rec >= 0 ? unpack_pwin(sh.rec[win_rec]) : sh.win;
         const int in_arc = ent.arc, a_src = ent.src, a_tgt = ent.tgt, a_cost = ent.cost, a_state = ent.state;
         const long long upper_in = ent.upper;
         const bool lower_state = a_state == STATE_LOWER;
@@ -961,7 +956,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 PROBE(13);
                 __syncthreads();
                 if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                if (tid == 0) { __threadfence(); st_vol_u32(P.done + (size_t)cta * 32, (unsigned)k); }
+                if (tid == kTT - 32) { __threadfence(); st_vol_u32(P.done + (size_t)cta * 32, (unsigned)k); }   // not a thread that polls ENTER next
                 PROBE(14);
             }
             TICK(t_update);
