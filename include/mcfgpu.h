@@ -167,6 +167,11 @@ int mcf_get_metrics(mcf_handle* h, mcf_metrics* out);             /* GetMetrics,
 /* Batches of independent instances (BASELINE.json config 5): instance i is solved on devices[i % n_devices],
  * one host thread per device.  statuses_out[count] receives each instance's mcf_status. */
 int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out);
+/* The same with `per_device` solves side by side on every GPU, each on its own stream over a 1/per_device share of the SMs
+ * (instance i runs on devices[i % n_devices]).  Worth it when an instance does not need the whole GPU: a 2^18-node
+ * instance occupies 37 of 148 SMs. */
+int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t per_device,
+                               int32_t* statuses_out);
 
 /* Roofline probe: uploads the handle's initial basis and runs the stand-alone Best Eligible pricing sweep
  * (one full pass over all S = m + n arcs, 16 B of arc data per arc) `reps` times, timing each launch with CUDA

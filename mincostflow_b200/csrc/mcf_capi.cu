@@ -781,26 +781,39 @@ int mcf_get_metrics(mcf_handle* h, mcf_metrics* out)
     *out = h->metrics; return MCF_OK;
 }
 
-int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out)
+int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t per_device, int32_t* statuses_out)
 {
-    if (!hs || count < 0 || !devices || n_devices <= 0) return MCF_ERR_INVALID_ARGUMENT;
-    std::vector<int> rcs(n_devices, MCF_OK);
+    if (!hs || count < 0 || !devices || n_devices <= 0 || per_device <= 0) return MCF_ERR_INVALID_ARGUMENT;
+    // `per_device` solves share one GPU: each is its own cooperative launch on its own stream over a 1 / per_device share of
+    // the SMs (a 2^18-node instance needs 37 CTAs, four run side by side on 148 SMs).  The solves are independent - no kernel
+    // ever waits for another one - so they may also simply run one after the other if the SMs are not free.
+    const int lanes = n_devices * per_device;
+    std::vector<int> rcs(lanes, MCF_OK);
     std::vector<std::thread> workers;
-    for (int d = 0; d < n_devices; ++d) {
-        workers.emplace_back([&, d]() {
-            for (int i = d; i < count; i += n_devices) {
-                if (!hs[i]) { rcs[d] = MCF_ERR_INVALID_ARGUMENT; continue; }
+    for (int w = 0; w < lanes; ++w) {
+        workers.emplace_back([&, w]() {
+            const int d = w % n_devices;
+            int sms = 0;
+            if (per_device > 1) { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, devices[d]) == cudaSuccess) sms = prop.multiProcessorCount; }
+            for (int i = w; i < count; i += lanes) {
+                if (!hs[i]) { rcs[w] = MCF_ERR_INVALID_ARGUMENT; continue; }
                 hs[i]->opt.device = devices[d];
+                if (per_device > 1 && sms > 0 && hs[i]->opt.max_ctas <= 0) hs[i]->opt.max_ctas = sms / per_device;
                 int32_t st = MCF_NOT_SOLVED;
                 const int rc = mcf_solve(hs[i], &st);
                 if (statuses_out) statuses_out[i] = st;
-                if (rc != MCF_OK && rcs[d] == MCF_OK) rcs[d] = rc;
+                if (rc != MCF_OK && rcs[w] == MCF_OK) rcs[w] = rc;
             }
         });
     }
     for (auto& w : workers) w.join();
-    for (int d = 0; d < n_devices; ++d) if (rcs[d] != MCF_OK) return rcs[d];
+    for (int w = 0; w < lanes; ++w) if (rcs[w] != MCF_OK) return rcs[w];
     return MCF_OK;
+}
+
+int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out)
+{
+    return mcf_solve_batch_concurrent(hs, count, devices, n_devices, 1, statuses_out);
 }
 
 int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_out, int32_t* entering_arc_out, int64_t* arcs_out)

@@ -1040,12 +1040,25 @@ extern "C" int mcfk_team_max_slice(int device, int wide)
     return (int)(s & ~7LL);
 }
 
+// the dynamic shared-memory ceiling of the kernel is always raised to the device's opt-in maximum: several host threads may
+// prepare launches with different slice sizes at the same time (mcf_solve_batch_concurrent)
+static cudaError_t raise_smem_limit(int device, int wide)
+{
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, team_fn(wide));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(team_fn(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes));
+}
+
 extern "C" int mcfk_team_max_ctas(int device, int slice, int wide)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
     const size_t smem = mcfk_team_smem_bytes(slice, wide);
-    if (cudaFuncSetAttribute(team_fn(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    if (raise_smem_limit(device, wide) != cudaSuccess) return -2;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, team_fn(wide), mcf::kTT, smem) != cudaSuccess) return -3;
     return per_sm * prop.multiProcessorCount;
@@ -1056,7 +1069,9 @@ extern "C" void mcfk_team_replicas(int* ent, int* cyc) { *ent = mcf::kRepEnt; *c
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream)
 {
     const size_t smem = mcfk_team_smem_bytes(p->slice, p->wide);
-    cudaError_t e = cudaFuncSetAttribute(team_fn(p->wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = raise_smem_limit(device, p->wide);
     if (e != cudaSuccess) return (int)e;
     void* args[] = {(void*)p};
     e = cudaLaunchCooperativeKernel(team_fn(p->wide), dim3(p->team), dim3(mcf::kTT), args, smem, stream);

@@ -138,7 +138,7 @@ class OptimizationConfig:
 _EXPORTS = ["mcf_api_version", "mcf_device_count", "mcf_default_options", "mcf_create", "mcf_destroy", "mcf_set_arcs",
             "mcf_set_supply", "mcf_set_options", "mcf_solve", "mcf_get_status", "mcf_get_flows", "mcf_get_potentials",
             "mcf_get_flow", "mcf_get_potential", "mcf_get_total_cost", "mcf_get_node_supply", "mcf_get_arc_cost",
-            "mcf_get_arc_lower_bound", "mcf_get_arc_upper_bound", "mcf_get_metrics", "mcf_solve_batch",
+            "mcf_get_arc_lower_bound", "mcf_get_arc_upper_bound", "mcf_get_metrics", "mcf_solve_batch", "mcf_solve_batch_concurrent",
             "mcf_pricing_probe", "mcf_last_error"]
 
 _lib = None
@@ -443,15 +443,15 @@ class NetworkSimplex:
         return ns.set_arrays(p.lower, p.upper, p.cost, p.supply)
 
 
-def solve_batch(solvers, devices):
-    """mcf_solve_batch: instance i runs on devices[i % len(devices)], one host thread per device."""
+def solve_batch(solvers, devices, per_device: int = 1):
+    """mcf_solve_batch[_concurrent]: instance i runs on devices[i % len(devices)], `per_device` solves side by side per GPU."""
     lib = load_library()
     for s in solvers:
         s._push(); s._flows = s._pots = None
     hs = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
     dev = (C.c_int32 * len(devices))(*devices)
     st = (C.c_int32 * len(solvers))()
-    rc = lib.mcf_solve_batch(hs, C.c_int32(len(solvers)), dev, C.c_int32(len(devices)), st)
+    rc = lib.mcf_solve_batch_concurrent(hs, C.c_int32(len(solvers)), dev, C.c_int32(len(devices)), C.c_int32(int(per_device)), st)
     if rc != 0:
         raise EngineError(rc, "; ".join((lib.mcf_last_error(s._h) or b"").decode() for s in solvers if lib.mcf_last_error(s._h)))
     return [SolverStatus(x) for x in st]

@@ -308,12 +308,15 @@ def test_pricing_probe_entering_arc_matches_oracle_first_pivot():
     assert arcs == p.n + p.m and arc == int(tin[0])
 
 
-def test_solve_batch_single_device():
-    ps = [instances.netgen8(10, seed=13502460 + i) for i in range(4)]
+@pytest.mark.parametrize("per_device", [1, 3])
+def test_solve_batch_single_device(per_device):
+    """mcf_solve_batch / mcf_solve_batch_concurrent: independent instances, `per_device` of them side by side on the GPU (each a
+    cooperative launch of its own over a share of the SMs)."""
+    ps = [instances.netgen8(12, seed=13502460 + i) for i in range(6)]
     solvers = [mcf.NetworkSimplex.from_problem(p) for p in ps]
     for s in solvers:
         s.SetOptimizationConfig(mcf.OptimizationConfig())
-    sts = mcf.solve_batch(solvers, [0])
+    sts = mcf.solve_batch(solvers, [0], per_device=per_device)
     for p, s, st in zip(ps, solvers, sts):
         r, rflow, rpi, _, _ = oracle.solve(p, config=oracle.default_config())
         assert int(st) == r.status == 1 and s.GetTotalCost() == r.total_cost
