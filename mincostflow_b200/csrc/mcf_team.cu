@@ -37,6 +37,7 @@ constexpr int kTW = kTT / 32;
 constexpr int kPf = 4;                                  // arcs per pricer thread staged ahead (2048 per pricing CTA)
 constexpr int kRepEnt = 4;                              // replicas of every ENTER record: a reader polls replica (cta % kRepEnt)
 constexpr int kRepCyc = 6;                              // replicas of every CYC record (fewer pollers per line, profiles/r01_micro_hop.txt)
+constexpr int kRelUnroll = 4;                            // nodes per thread in flight in the relabel pass
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
 __device__ __forceinline__ int4 ld_vol4(const int4* p)
@@ -932,12 +933,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (change) {
                     const int sh_lo = b < a ? b + 1 : a + s, sh_len = b < a ? a - b - 1 : b - a - s + 1, sh_by = b < a ? s : -s;
                     // consecutive lanes <-> consecutive nodes (the mirror stores coalesce), four independent nodes per thread in flight
-                    for (int j0 = tid; j0 < cntn; j0 += 4 * kTT) {
-                        int xv[4];
+                    for (int j0 = tid; j0 < cntn; j0 += kRelUnroll * kTT) {
+                        int xv[kRelUnroll];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { const int j = j0 + e * kTT; xv[e] = j < cntn ? in_s[j] : 0; }
+                        for (int e = 0; e < kRelUnroll; ++e) { const int j = j0 + e * kTT; xv[e] = j < cntn ? in_s[j] : 0; }
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
+                        for (int e = 0; e < kRelUnroll; ++e) {
                             const int x = xv[e], j = j0 + e * kTT;
                             if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {                // between the old and the new place: shift
                                 in_s[j] = x + sh_by; P.node[lo + j].in = x + sh_by;
