@@ -320,9 +320,9 @@ int choose_team(mcf_handle* h, int wide, int* slice_out, int* pricers_out)
     const long long S = (long long)h->m + h->n;
     const long long need = (nodes + max_slice - 1) / max_slice;                 // owners the slices need at least
     if (need > limit - 1) return 0;
-    // pricers: one SM is gather-bound on a whole block; ~384 arcs of the first block per pricer
+    // pricers: one SM is gather-bound on a whole block; ~192 arcs of the first block per pricer (each arc end costs two L1TEX line look-ups)
     const long long B = (long long)std::sqrt((double)S);
-    long long pricers = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (B + 383) / 384;
+    long long pricers = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (B + 191) / 192;
     if (pricers < 1) pricers = 1;
     if (pricers > mcf::kMaxPricers) pricers = mcf::kMaxPricers;
     if (pricers > limit - need) pricers = limit - need;
@@ -344,7 +344,12 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
-    CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_node.ensure(n + 1));
+    CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1));
+    // node mirror {pi, depth} and the dense label array live in ONE allocation so that a single L2 access-policy window can
+    // keep both resident (the arc arrays stream through L2 and would otherwise evict them between two uses of a record)
+    const size_t mirror_recs = (size_t)(n + 1) + ((size_t)(n + 1) * 4 + sizeof(mcf::NodeRec) - 1) / sizeof(mcf::NodeRec);
+    CUDA_TRY(h, h->d_node.ensure(mirror_recs));
+    int* const d_in_g = reinterpret_cast<int*>(h->d_node.p + (n + 1));
     CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)(team + pricers) * 32));     // DONE flags of the owners + GATHERED flags of the pricers
     int rep_ent = 1, rep_cyc = 1;
     mcfk_team_replicas(&rep_ent, &rep_cyc);
@@ -363,6 +368,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     CUDA_TRY(h, up(h->d_flow.p, h->h_flow.data(), (size_t)A * 8)); CUDA_TRY(h, up(h->d_upper.p, h->h_upper.data(), (size_t)A * 8));
     CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4));
     CUDA_TRY(h, up(h->d_node.p, h->h_node.data(), (size_t)(n + 1) * sizeof(mcf::NodeRec)));
+    CUDA_TRY(h, up(d_in_g, h->h_in.data(), (size_t)(n + 1) * 4));
     CUDA_TRY(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(mcf::Ctl), st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)(team + pricers) * 32 * sizeof(unsigned), st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_mail.p, 0, (seg_off + w_seg + 8) * sizeof(int4), st));
@@ -370,7 +376,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     std::memset(P, 0, sizeof(*P));
     P->n = n; P->m = m; P->S = S; P->A = A;
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
-    P->node = h->d_node.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
+    P->node = h->d_node.p; P->in_g = d_in_g; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
     P->ent0 = h->d_mail.p; P->prc = P->ent0 + w_ent; P->late = P->prc + w_pr; P->cyc = P->late + w_late;
     P->stemhdr = P->cyc + w_cyc; P->stemseg = h->d_mail.p + seg_off;
     P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
@@ -406,6 +412,23 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     const double tmo = h->opt.barrier_timeout_s > 0 ? h->opt.barrier_timeout_s : 10.0;
     P.timeout_cycles = (unsigned long long)(tmo * 1.9e9);
 
+    {   // keep the node mirror L2-resident (persisting lines), everything else on this stream streams through
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, h->opt.device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->opt.device);
+        const size_t mirror_bytes = (size_t)(n + 1) * (sizeof(mcf::NodeRec) + 4);
+        if (max_win > 0 && max_persist > 0) {
+            const size_t want = std::min<size_t>(mirror_bytes + (1u << 20), (size_t)max_persist);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = h->d_node.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(mirror_bytes, (size_t)max_win);
+            av.accessPolicyWindow.hitRatio = mirror_bytes <= want ? 1.0f : (float)((double)want / (double)mirror_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+    }
     cudaEvent_t ev0, ev1;
     CUDA_TRY(h, cudaEventCreate(&ev0)); CUDA_TRY(h, cudaEventCreate(&ev1));
     CUDA_TRY(h, cudaEventRecord(ev0, h->stream));

@@ -99,7 +99,8 @@ struct Params {
 
 struct __align__(16) NodeRec {          // global mirror of a node, read by the pricing gathers (one 128-bit load)
     long long pi;                       // potential (NS.cs:48)
-    int in;                             // current depth-first index of the node in the basis tree
+    int in;                             // initial depth-first index (the live one is the dense array TeamParams::in_g: a third of
+                                        // all labels shift on every pivot, and 4-byte-stride stores cost a quarter of the sectors)
     int dp;                             // current depth of the node (root = 0)
 };
 
@@ -118,7 +119,8 @@ struct TeamParams {
     long long* flow;                                     // [A]
     const long long* upper;                              // [A]
     const long long* orig_lower;                         // [m] or nullptr
-    NodeRec* node;                                       // [n+1] (root = n)
+    NodeRec* node;                                       // [n+1] (root = n): pi and depth
+    int* in_g;                                           // [n+1] current depth-first index of every node
     const int* sz0; const int* pd0;                      // [n+1] initial basis
     long long* pi_out;                                   // [n]
     int4* ent0;                                          // [2][pricers][kMailWords]  pricer -> all: its part of the first block

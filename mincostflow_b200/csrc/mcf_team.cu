@@ -105,6 +105,7 @@ struct PWin {                       // a pricing candidate
     long long rc;
     int off;                        // scan offset from next_arc (< 0: none)
     int arc, src, tgt, cost, state, in_s, in_t, dp_s, dp_t;
+    int blk;                        // block of the scan the candidate lies in (later rounds of a search)
     long long pi_s, pi_t, upper;
 };
 
@@ -181,7 +182,7 @@ __device__ __forceinline__ void post_pwin(int4* rec, const PWin& w, int round, i
     else if (lane == 2) o = make_int4(lo32(w.pi_s), hi32(w.pi_s), w.in_s, seq);
     else if (lane == 3) o = make_int4(lo32(w.pi_t), hi32(w.pi_t), w.in_t, seq);
     else if (lane == 4) o = make_int4(lo32(w.upper), hi32(w.upper), w.off, seq);
-    else if (lane == 5) o = make_int4(lo32(w.rc), hi32(w.rc), 0, seq);
+    else if (lane == 5) o = make_int4(lo32(w.rc), hi32(w.rc), w.blk, seq);
     else o = make_int4(w.dp_s, w.dp_t, 0, seq);
     st_vol4(rec + lane, o);
 }
@@ -191,12 +192,12 @@ __device__ __forceinline__ PWin unpack_pwin(const int4* r)
     w.arc = r[0].x; w.src = r[0].y; w.tgt = r[0].z; w.cost = r[1].x; w.state = r[1].y;
     w.pi_s = mk64(r[2].x, r[2].y); w.in_s = r[2].z; w.pi_t = mk64(r[3].x, r[3].y); w.in_t = r[3].z;
     w.upper = mk64(r[4].x, r[4].y); w.off = r[0].x >= 0 ? r[4].z : -1; w.rc = mk64(r[5].x, r[5].y);
-    w.dp_s = r[6].x; w.dp_t = r[6].y;
+    w.dp_s = r[6].x; w.dp_t = r[6].y; w.blk = r[5].z;
     return w;
 }
 __device__ __forceinline__ PWin pwin_none()
 {
-    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = w.dp_s = w.dp_t = 0; w.pi_s = w.pi_t = w.upper = 0;
+    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = w.dp_s = w.dp_t = w.blk = 0; w.pi_s = w.pi_t = w.upper = 0;
     return w;
 }
 __device__ __forceinline__ Cand cand_none() { Cand c; c.d = 0; c.in = c.sz = c.zero = c.dp = c.j = 0; c.pd = -1; return c; }
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         for (int j = tid; j < cntn; j += kTT) {
             const int u = lo + j;
             const int pd = P.pd0[u];
-            in_s[j] = P.node[u].in; dp_s[j] = P.node[u].dp; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
+            in_s[j] = P.in_g[u]; dp_s[j] = P.node[u].dp; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
             const long long fl = pd >= 0 ? P.flow[pd >> 1] : 0, up = pd >= 0 ? P.upper[pd >> 1] : 0;
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
@@ -358,8 +359,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (off < s_hi) {
                 const int4 rs = __ldcg(reinterpret_cast<const int4*>(P.node + pf_src[q]));
                 const int4 rt = __ldcg(reinterpret_cast<const int4*>(P.node + pf_tgt[q]));
-                pf_pis[q] = mk64(rs.x, rs.y); pf_ins[q] = rs.z; pf_dps[q] = rs.w;
-                pf_pit[q] = mk64(rt.x, rt.y); pf_int[q] = rt.z; pf_dpt[q] = rt.w;
+                const int is = __ldcg(P.in_g + pf_src[q]), it = __ldcg(P.in_g + pf_tgt[q]);
+                pf_pis[q] = mk64(rs.x, rs.y); pf_ins[q] = is; pf_dps[q] = rs.w;
+                pf_pit[q] = mk64(rt.x, rt.y); pf_int[q] = it; pf_dpt[q] = rt.w;
             }
         }
     };
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // ================================================================ pricers: price their share of the first block, post
         if (pricer) {
             TICK(t_wdone);
-            PROBE(0);
+            if (tid == 0 && cta == 0) sh.bk.pr_mark = (unsigned long long)clock64();
             // ---- round 0 of BlockSearchPivot.FindEnteringArc (NS.cs:1339-1397): the first block, split over the pricers.
             // The share was staged (arc data + both ends' node records) BEFORE the previous pivot's update was applied; that
             // one update is replayed here from its closed form (sh.pend), so pricing does not wait for hop 3.
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     const long long rc = (long long)st * ((long long)c + ps - pt);
                     if (rc < best.rc) {
                         best.rc = rc; best.off = off; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
-                        best.in_s = rs.z; best.in_t = rt.z; best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt; best.upper = up;
+                        best.in_s = __ldcg(P.in_g + s); best.in_t = __ldcg(P.in_g + t); best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt; best.upper = up;
                     }
                 }
                 const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
@@ -522,19 +524,24 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         }
         if (!have_win) {
             if (pricer) {
-                // ---- later rounds: pricer p prices block 1 + (r-1)*NP + p straight from global memory (every update visible first);
-                // the lowest block with a negative reduced cost wins
+                // ---- later rounds, straight from global memory (every update visible first): in round r each pricer prices M
+                // consecutive blocks (M = 1, 2, 4, ... while NP*M <= 16), NP*M blocks per exchange; the lowest block with a negative reduced
+                // cost wins, inside it the smallest reduced cost, then the first in scan order
                 if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 const long long nblk = ((long long)S + B - 1) / B;
+                long long next_blk = 1;
                 int found_blk = -1;
                 for (int r = 1; found_blk < 0; ++r) {
-                    const long long first_blk = 1 + (long long)(r - 1) * NP;
-                    if (first_blk >= nblk) break;
-                    const long long blk = first_blk + cta;
+                    if (next_blk >= nblk) break;
+                    const int mcap = NP >= 16 ? 1 : 16 / NP;                         // about 16 blocks per exchange at most
+                    const int M = min(mcap, r < 4 ? 1 << (r - 1) : 8);
+                    const long long b_lo = next_blk + (long long)cta * M, b_hi = min(nblk, b_lo + M);
                     PWin best = pwin_none();
-                    if (blk < nblk) {
-                        const long long o_lo = blk * B; long long o_hi = o_lo + B; if (o_hi > S) o_hi = S;
+                    if (b_lo < nblk) {
+                        const long long o_lo = b_lo * B; long long o_hi = b_hi * B; if (o_hi > S) o_hi = S;
                         for (long long off = o_lo + tid; off < o_hi; off += kTT) {
+                            const int blk = M == 1 ? (int)b_lo : (int)(off / B);
+                            if (best.off >= 0 && blk > best.blk) break;             // a thread's offsets ascend: later blocks cannot win
                             int idx = next_arc + (int)off; if (idx >= S) idx -= S;
                             const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
                             const int st = fix_state(idx, __ldcg(P.state + idx));
@@ -543,19 +550,24 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const long long ps = mk64(rs.x, rs.y), pt = mk64(rt.x, rt.y);
                             const long long rc = (long long)st * ((long long)c + ps - pt);
                             if (rc < best.rc) {
-                                best.rc = rc; best.off = (int)off; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
-                                best.in_s = rs.z; best.in_t = rt.z; best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt;
+                                best.rc = rc; best.off = (int)off; best.blk = blk; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
+                                best.in_s = __ldcg(P.in_g + s); best.in_t = __ldcg(P.in_g + t); best.dp_s = rs.w; best.dp_t = rt.w; best.pi_s = ps; best.pi_t = pt;
                             }
                         }
                     }
                     __syncthreads();                                    // sh.pw / sh.rec of the previous round are consumed
-                    const int wl = warp_argmin(best.off >= 0, best.rc, best.off);
-                    if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
-                    else if (lane == wl) { best.upper = __ldg(P.upper + best.arc); sh.pw[warp] = best; }
+                    {   // lowest block first, then (rc, off)
+                        const int mb = __reduce_min_sync(0xffffffffu, best.off >= 0 ? best.blk : INT_MAX);
+                        const int wl = warp_argmin(best.off >= 0 && best.blk == mb, best.rc, best.off);
+                        if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
+                        else if (lane == wl) { best.upper = __ldg(P.upper + best.arc); sh.pw[warp] = best; }
+                    }
                     __syncthreads();
                     if (warp == 0) {
                         const PWin* q = &sh.pw[lane & (kTW - 1)];
-                        const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
+                        const bool qv = lane < kTW && q->off >= 0;
+                        const int mb = __reduce_min_sync(0xffffffffu, qv ? q->blk : INT_MAX);
+                        const int ww = warp_argmin(qv && q->blk == mb, q->rc, q->off);
                         PWin mine = pwin_none();
                         if (ww >= 0) mine = sh.pw[ww];
                         // words 0, 2..6 first, one fence, then word 1 (which carries the round) as the flag: a round record
@@ -578,7 +590,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     __syncthreads();
                     if (sh.abort) break;
                     if (tid == 0) sh.bk.rounds_total++;
-                    for (int p = 0; p < NP; ++p) if (sh.rec[p][0].x >= 0) { found_blk = (int)(first_blk + p); if (tid == 0) sh.win = unpack_pwin(sh.rec[p]); break; }
+                    // pricer p holds blocks below those of pricer p+1: the first record with a candidate is the lowest block
+                    for (int p = 0; p < NP; ++p) if (sh.rec[p][0].x >= 0) { found_blk = sh.rec[p][5].z; if (tid == 0) sh.win = unpack_pwin(sh.rec[p]); break; }
+                    next_blk += (long long)NP * M;
                 }
                 if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (found_blk >= 0) {
@@ -642,11 +656,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 stage_static_begin(next_arc, s_lo, s_hi, stv);
             }
             spec_cursor = -1;
+            PROBE(3);
             if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            if (fits) { stage_static_finish(s_lo, s_hi, stv); stage_gather(s_lo, s_hi); pf_next = next_arc; pf_B = B; pf_upto = k - 1; } else pf_next = -1;
+            PROBE(6);
+            if (fits) { stage_static_finish(s_lo, s_hi, stv); PROBE(0); stage_gather(s_lo, s_hi); pf_next = next_arc; pf_B = B; pf_upto = k - 1; } else pf_next = -1;
             __syncthreads();
             if (tid == 0) st_vol_u32(P.done + (size_t)(G + cta) * 32, (unsigned)(k + 1));      // GATHERED(k+1)
-            PROBE(3);
+            PROBE(7);
         } else PROBE(9);
 
         const PWin ent = win_rec >= 0 ? unpack_pwin(sh.rec[win_rec]) : sh.win;
@@ -941,13 +957,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         for (int e = 0; e < kRelUnroll; ++e) {
                             const int x = xv[e], j = j0 + e * kTT;
                             if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {                // between the old and the new place: shift
-                                in_s[j] = x + sh_by; P.node[lo + j].in = x + sh_by;
+                                in_s[j] = x + sh_by; P.in_g[lo + j] = x + sh_by;
                             } else if ((unsigned)(x - a) < (unsigned)s) {                  // re-hung subtree
                                 int nx, nd;
                                 relabel(U, x, dp_s[j], nx, nd);
                                 in_s[j] = nx; dp_s[j] = nd;
                                 atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)U.sigma);
-                                *reinterpret_cast<int2*>(&P.node[lo + j].in) = make_int2(nx, nd);
+                                P.in_g[lo + j] = nx; P.node[lo + j].dp = nd;
                             }
                         }
                     }
