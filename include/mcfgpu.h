@@ -180,6 +180,12 @@ int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* de
 int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_out, int32_t* entering_arc_out,
                       int64_t* arcs_per_launch_out);
 
+/* SolutionValidator.Validate() (Lemon/Validation/SolutionValidator.cs:20-53) on the device, over the arrays the solve left
+ * in HBM: *failed_checks_out is a bit set - 1 flow conservation (:55-100), 2 capacity bounds (:102-125), 4 complementary
+ * slackness (:135-176), 8 dual feasibility of the supply form (:191-231), 16 objective != sum flow*cost (:234-262),
+ * 32 dual objective != primal (:268-342); 0 = IsValid.  MCF_ERR_NOT_OPTIMAL unless Status == Optimal (:24-33). */
+int mcf_validate(mcf_handle* h, int32_t* failed_checks_out, int64_t* primal_objective_out, int64_t* dual_objective_out);
+
 const char* mcf_last_error(mcf_handle* h);
 
 #ifdef __cplusplus

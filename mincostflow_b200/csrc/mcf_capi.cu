@@ -24,6 +24,7 @@ extern "C" int mcfk_pivot_smem_bytes();
 extern "C" int mcfk_max_grid(int device, int* sm_count);
 extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
+extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaStream_t stream);
 extern "C" size_t mcfk_team_smem_bytes(int slice, int wide);
 extern "C" int mcfk_team_max_slice(int device, int wide);
 extern "C" int mcfk_team_max_ctas(int device, int slice, int wide);
@@ -81,6 +82,9 @@ struct mcf_handle {
     DevBuf<mcf::CycEnt> d_list;
     DevBuf<mcf::Ctl> d_ctl;
     DevBuf<unsigned char> d_flush;
+    DevBuf<long long> d_val;                                          // validator scratch
+    const long long* d_pi_final = nullptr;                            // potentials of the last solve, device side
+    int supply_type_solved = 0;
     // team engine (mcf_team.cu)
     DevBuf<mcf::NodeRec> d_node;
     DevBuf<int4> d_mail;                                              // enter | cyc | stemhdr | stemseg
@@ -212,7 +216,7 @@ int bind_device(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release();
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->device_bound = dev;
     }
@@ -467,7 +471,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     M.degenerate_pivots = ctl.degenerate; M.cycle_nodes = ctl.cycle_nodes; M.moved_nodes = ctl.moved_nodes;
     M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
     M.arcs_priced = ctl.arcs_checked; M.pricing_bytes = 16 * M.arcs_priced; M.engine = 2;
-    h->total_cost = ctl.total_cost;
+    h->total_cost = ctl.total_cost; h->d_pi_final = h->d_piout.p; h->supply_type_solved = h->opt.supply_type;
 
     if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots", (long long)ctl.iterations); }
     if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
@@ -541,7 +545,7 @@ void mcf_destroy(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release();
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -582,6 +586,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     const auto t_total = clk::now();
     h->metrics = mcf_metrics{};
     h->status = MCF_NOT_SOLVED;
+    h->d_pi_final = nullptr;
     const int n = h->n, m = h->m, S = m + n;
     auto done = [&](int st) { h->status = st; h->solved_once = true; if (status_out) *status_out = st; h->metrics.total_solve_time_us = us_since(t_total); return MCF_OK; };
 
@@ -713,7 +718,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     else if (kind == mcf::PK_FIRST) M.arcs_priced = 0;       // not tracked for First Eligible
     else M.arcs_priced = ctl.arcs_checked;
     M.pricing_bytes = 16 * M.arcs_priced; M.engine = 1;
-    h->total_cost = ctl.total_cost;
+    h->total_cost = ctl.total_cost; h->d_pi_final = h->d_pi.p; h->supply_type_solved = h->opt.supply_type;
 
     if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "grid barrier timed out after %lld pivots", (long long)ctl.iterations); }
     if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
@@ -844,6 +849,7 @@ int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_o
     if (!h || reps <= 0 || !ms_out) return MCF_ERR_INVALID_ARGUMENT;
     int rc = bind_device(h);
     if (rc != MCF_OK) return rc;
+    h->d_pi_final = nullptr;                                    // the probe re-uploads the initial basis over the solve's arrays
     const int n = h->n, m = h->m, S = m + n;
     // same pre-pass as mcf_solve, on copies: the probe must not disturb the handle's problem data
     std::vector<int64_t> sv_supply = h->supply, sv_upper = h->upper;
@@ -881,6 +887,46 @@ int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_o
     for (int g = 0; g < grid; ++g) if (recs[g].c < bc || (recs[g].c == bc && recs[g].c < 0 && recs[g].arc < ba)) { bc = recs[g].c; ba = recs[g].arc; }
     if (entering_arc_out) *entering_arc_out = ba;
     if (arcs_out) *arcs_out = S;
+    return MCF_OK;
+}
+
+int mcf_validate(mcf_handle* h, int32_t* failed_checks_out, int64_t* primal_out, int64_t* dual_out)
+{
+    if (!h || !failed_checks_out) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");        // SolutionValidator.cs:24-33
+    const int n = h->n, m = h->m;
+    if (n == 0) { *failed_checks_out = 0; if (primal_out) *primal_out = 0; if (dual_out) *dual_out = 0; return MCF_OK; }
+    if (!h->d_pi_final) return fail(h, MCF_ERR_NOT_SOLVED, "the solve's arrays are no longer resident on the device (a pricing probe ran since)");
+    CUDA_TRY(h, cudaSetDevice(h->device_bound));
+    // device-resident from the solve: src, tgt, cost (int32), flow (final, lower bounds restored), pi.  Uploaded here: the
+    // caller's bounds and supplies (h->upper is shifted by the lower bound after Solve(), NS.cs:647-651; undo that).
+    const size_t words = (size_t)3 * m + (size_t)3 * n + 8;
+    CUDA_TRY(h, h->d_val.ensure(words));
+    long long* d_lower = h->d_val.p; long long* d_upper = d_lower + m; long long* d_supply = d_upper + m;
+    long long* d_net = d_supply + n; long long* d_adj = d_net + n; long long* d_out = d_adj + n;
+    std::vector<int64_t> up(m);
+    for (int i = 0; i < m; ++i) up[i] = h->upper[i] >= kInf ? h->upper[i] : h->upper[i] + h->orig_lower[i];
+    CUDA_TRY(h, cudaMemcpyAsync(d_lower, h->orig_lower.data(), (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_upper, up.data(), (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_supply, h->supply.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(d_net, 0, ((size_t)2 * n + 8) * 8, h->stream));
+    mcf::ValidateParams V{};
+    V.n = n; V.m = m; V.supply_type = h->supply_type_solved;
+    V.src = h->d_src.p; V.tgt = h->d_tgt.p; V.cost = h->d_cost.p; V.flow = h->d_flow.p; V.lower = d_lower; V.upper = d_upper;
+    V.supply = d_supply; V.pi = h->d_pi_final; V.net = d_net; V.adj = d_adj; V.out = d_out;
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device_bound));
+    const int lrc = mcfk_launch_validate(&V, prop.multiProcessorCount, h->stream);
+    if (lrc != 0) return fail(h, MCF_ERR_CUDA, "validator launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+    long long out[3] = {0, 0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int bad = (int)out[0];
+    if (out[1] != h->total_cost) bad |= 16;                                                          // SolutionValidator.cs:234-262
+    if (out[2] != h->total_cost) bad |= 32;                                                          // :268-342
+    *failed_checks_out = bad;
+    if (primal_out) *primal_out = out[1];
+    if (dual_out) *dual_out = out[2];
     return MCF_OK;
 }
 

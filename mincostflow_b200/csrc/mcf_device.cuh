@@ -141,4 +141,12 @@ struct TeamParams {
     unsigned long long timeout_cycles;
 };
 
+// SolutionValidator on the device (mcf_kernels.cu)
+struct ValidateParams {
+    int n, m, supply_type;
+    const int* src; const int* tgt; const int* cost;
+    const long long* flow; const long long* lower; const long long* upper; const long long* supply; const long long* pi;
+    long long* net; long long* adj; long long* out;
+};
+
 }  // namespace mcf

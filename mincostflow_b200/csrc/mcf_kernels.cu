@@ -592,6 +592,57 @@ __global__ void __launch_bounds__(kThreads, 1) ns_price_sweep_kernel(const Param
     if (tid == 0) { PriceRec r; r.c = best.a; r.arc = best.a < 0 ? best.b : -1; r.src = r.tgt = r.cost = r.state = r.off = 0; out[cta] = r; }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SolutionValidator (Lemon/Validation/SolutionValidator.cs:20-342) as two streaming reductions over the arrays the solve
+// left in HBM: flow conservation (:55-100), bounds (:102-125), complementary slackness (:135-176), dual feasibility of the
+// supply form (:191-231), objective (:234-262) and dual objective (:268-342).  out: [0] failed-check bits, [1] primal
+// objective sum(flow*cost), [2] dual objective.  net[] / adj[] are int64 scratch of n entries, zeroed by the caller.
+__global__ void __launch_bounds__(256) ns_validate_arcs_kernel(const ValidateParams V)
+{
+    long long primal = 0, dual = 0;
+    int bad = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < V.m; e += gridDim.x * blockDim.x) {
+        const int s = __ldg(V.src + e), t = __ldg(V.tgt + e);
+        const long long c = __ldg(V.cost + e), f = __ldg(V.flow + e), lo = __ldg(V.lower + e), up = __ldg(V.upper + e);
+        const long long rc = c + __ldg(V.pi + s) - __ldg(V.pi + t);
+        if (f < lo || f > up) bad |= 2;
+        if (rc > 0 && f != lo) bad |= 4;
+        if (rc < 0 && f != up) bad |= 4;
+        primal += f * c;
+        if (f != 0) { atomicAdd(reinterpret_cast<unsigned long long*>(V.net + s), (unsigned long long)f); atomicAdd(reinterpret_cast<unsigned long long*>(V.net + t), (unsigned long long)(-f)); }
+        if (lo != 0) { dual += lo * c; atomicAdd(reinterpret_cast<unsigned long long*>(V.adj + s), (unsigned long long)(-lo)); atomicAdd(reinterpret_cast<unsigned long long*>(V.adj + t), (unsigned long long)lo); }
+        if (rc < 0) dual -= (up - lo) * -rc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        primal += __shfl_xor_sync(0xffffffffu, primal, o); dual += __shfl_xor_sync(0xffffffffu, dual, o); bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(reinterpret_cast<unsigned long long*>(V.out), (unsigned long long)bad);
+        if (primal) atomicAdd(reinterpret_cast<unsigned long long*>(V.out + 1), (unsigned long long)primal);
+        if (dual) atomicAdd(reinterpret_cast<unsigned long long*>(V.out + 2), (unsigned long long)dual);
+    }
+}
+
+__global__ void __launch_bounds__(256) ns_validate_nodes_kernel(const ValidateParams V)
+{
+    long long dual = 0;
+    int bad = 0;
+    const bool geq = V.supply_type == 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V.n; i += gridDim.x * blockDim.x) {
+        const long long net = V.net[i], sup = __ldg(V.supply + i), p = __ldg(V.pi + i);
+        if (geq ? net < sup : net > sup) bad |= 1;
+        if (geq) { if (p > 0 || (p < 0 && net != sup)) bad |= 8; }
+        else     { if (p < 0 || (p > 0 && net != sup)) bad |= 8; }
+        dual -= (sup + V.adj[i]) * p;
+    }
+    for (int o = 16; o > 0; o >>= 1) { dual += __shfl_xor_sync(0xffffffffu, dual, o); bad |= __shfl_xor_sync(0xffffffffu, bad, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(reinterpret_cast<unsigned long long*>(V.out), (unsigned long long)bad);
+        if (dual) atomicAdd(reinterpret_cast<unsigned long long*>(V.out + 2), (unsigned long long)dual);
+    }
+}
+
 }  // namespace mcf
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -619,6 +670,14 @@ extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t st
     void* args[] = {(void*)p};
     e = cudaLaunchCooperativeKernel((const void*)mcf::ns_pivot_kernel, dim3(grid), dim3(mcf::kThreads), args, smem, stream);
     return (int)e;
+}
+
+extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaStream_t stream)
+{
+    const int grid = sms * 8;
+    mcf::ns_validate_arcs_kernel<<<grid, 256, 0, stream>>>(*v);
+    mcf::ns_validate_nodes_kernel<<<grid, 256, 0, stream>>>(*v);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream)

@@ -139,7 +139,7 @@ _EXPORTS = ["mcf_api_version", "mcf_device_count", "mcf_default_options", "mcf_c
             "mcf_set_supply", "mcf_set_options", "mcf_solve", "mcf_get_status", "mcf_get_flows", "mcf_get_potentials",
             "mcf_get_flow", "mcf_get_potential", "mcf_get_total_cost", "mcf_get_node_supply", "mcf_get_arc_cost",
             "mcf_get_arc_lower_bound", "mcf_get_arc_upper_bound", "mcf_get_metrics", "mcf_solve_batch", "mcf_solve_batch_concurrent",
-            "mcf_pricing_probe", "mcf_last_error"]
+            "mcf_pricing_probe", "mcf_validate", "mcf_last_error"]
 
 _lib = None
 
@@ -426,6 +426,13 @@ class NetworkSimplex:
             self._check(self._lib.mcf_get_potentials(self._h, _ptr(out)))
             self._pots = out
         return self._pots
+
+    def Validate(self):
+        """SolutionValidator(graph, solver).Validate() on the device (mcf_validate).  Returns (failed-check bits, primal, dual);
+        bits == 0 is `IsValid`."""
+        bad = C.c_int32(0); primal = C.c_int64(0); dual = C.c_int64(0)
+        self._check(self._lib.mcf_validate(self._h, C.byref(bad), C.byref(primal), C.byref(dual)))
+        return bad.value, primal.value, dual.value
 
     def pricing_probe(self, reps=5, flush_l2=True):
         """Stand-alone Best Eligible sweep over all S arcs (mcf_pricing_probe).  Returns (ms per launch, arc, S)."""

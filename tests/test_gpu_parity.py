@@ -308,6 +308,41 @@ def test_pricing_probe_entering_arc_matches_oracle_first_pivot():
     assert arcs == p.n + p.m and arc == int(tin[0])
 
 
+def test_device_validator_matches_the_restated_solution_validator(golden, load_fixture):
+    """mcf_validate = SolutionValidator.cs as a device reduction over the arrays the solve left in HBM: same verdict bits and
+    dual objective as the CPU restatement, on valid solutions and on a deliberately broken one."""
+    import ctypes as C
+    names = ["netgen_8_10a", "transport_40x30", "circulation_100_0_10", "assignment_50x50", "grid_5x5", "AllBookingsShouldScheduleIllustration"]
+    for name in names:
+        p = load_fixture(name)
+        ns = mcf.NetworkSimplex.from_problem(p)
+        assert ns.Solve() == mcf.SolverStatus.Optimal
+        bad, primal, dual = ns.Validate()
+        obad, odual = oracle.validate(p, ns.flows(), ns.potentials(), ns.GetTotalCost())
+        assert (bad, dual) == (obad, odual) == (0, ns.GetTotalCost()) and primal == ns.GetTotalCost(), name
+    for case in golden["lemon_cases"]:                                   # lower bounds, LEQ form
+        p, stype, status, total = lemon_case_problem(golden, case)
+        ns = mcf.NetworkSimplex.from_problem(p)
+        ns.SetSupplyType(stype)
+        if ns.Solve() != mcf.SolverStatus.Optimal:
+            with pytest.raises(mcf.InvalidOperationException):
+                ns.Validate()
+            continue
+        bad, primal, dual = ns.Validate()
+        obad, odual = oracle.validate(p, ns.flows(), ns.potentials(), ns.GetTotalCost(), supply_type=stype)
+        assert (bad, dual) == (obad, odual), (case[0], bad, obad, dual, odual)
+    # break it: claim a different supply after the solve - conservation and the dual objective must fail identically
+    p = load_fixture("netgen_8_08a")
+    ns = mcf.NetworkSimplex.from_problem(p)
+    assert ns.Solve() == mcf.SolverStatus.Optimal
+    sup = p.supply.copy(); i = int(np.nonzero(sup > 0)[0][0]); sup[i] += 7
+    ns._check(ns._lib.mcf_set_supply(ns._h, sup.ctypes.data_as(C.c_void_p)))
+    bad, primal, dual = ns.Validate()
+    q = Problem(p.n, p.m, p.source, p.target, p.lower, p.upper, p.cost, sup, "netgen_8_08a_wrong_supply")
+    obad, odual = oracle.validate(q, ns.flows(), ns.potentials(), ns.GetTotalCost())
+    assert bad == obad != 0 and dual == odual
+
+
 @pytest.mark.parametrize("per_device", [1, 3])
 def test_solve_batch_single_device(per_device):
     """mcf_solve_batch / mcf_solve_batch_concurrent: independent instances, `per_device` of them side by side on the GPU (each a
