@@ -40,6 +40,7 @@ namespace MinCostFlow.Core.Cuda
         [DllImport(Lib)] internal static extern int mcf_get_flows(IntPtr h, long* outM);
         [DllImport(Lib)] internal static extern int mcf_get_potentials(IntPtr h, long* outN);
         [DllImport(Lib)] internal static extern int mcf_get_total_cost(IntPtr h, out long cost);
+        [DllImport(Lib)] internal static extern int mcf_validate(IntPtr h, out int failedChecks, out long primal, out long dual);
         [DllImport(Lib)] internal static extern IntPtr mcf_last_error(IntPtr h);
     }
 
@@ -107,6 +108,10 @@ namespace MinCostFlow.Core.Cuda
         public long GetFlow(Arc arc) { RequireOptimal(); CheckArc(arc); return _flow[arc.Id]; }               // NetworkSimplex.cs:416-431
         public long GetPotential(Node node) { RequireOptimal(); if (!_graph.IsValidNode(node)) throw new ArgumentException("Invalid node"); return _pi[node.Id]; }
         public long GetTotalCost() { RequireOptimal(); return _totalCost; }
+
+        /// <summary>SolutionValidator.Validate() on the device; 0 = valid, else bits 1 conservation, 2 bounds, 4 complementary
+        /// slackness, 8 dual feasibility, 16 objective, 32 dual objective (SolutionValidator.cs:20-342).</summary>
+        public int ValidateOnDevice(out long primal, out long dual) { RequireOptimal(); Check(Native.mcf_validate(_h, out int bad, out primal, out dual)); return bad; }
 
         private void RequireOptimal() { if (Status != SolverStatus.Optimal) throw new InvalidOperationException("Solution not optimal"); }
         private void CheckArc(Arc arc) { if (!_graph.IsValidArc(arc)) throw new ArgumentException("Invalid arc"); }
