@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const bool fits = share(B, s_lo, s_hi);
             PWin best = pwin_none();
             if (fits) {
-                if (!(pf_next == next_arc && pf_B == B)) {               // nothing usable staged (first use of a new block size): stage now
+                if (!(pf_next == next_arc && pf_B == B)) [[unlikely]] {               // nothing usable staged (first use of a new block size): stage now
                     if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                     stage_static(next_arc, s_lo, s_hi); stage_gather(s_lo, s_hi);
                     pf_next = next_arc; pf_B = B; pf_upto = k - 1;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     }
                     sh.pw[warp] = best;
                 }
-            } else {
+            } else [[unlikely]] {
                 // share larger than the staging area (B > pricers x 2048): price straight from global memory
                 if (!wait_done(k - 1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 for (int off = s_lo + tid; off < s_hi; off += kTT) {
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 else if (lane == wl) sh.pw[warp] = best;
             }
             __syncthreads();
-            if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
             if (warp == 0) {                                             // CTA arg-min of (rc, off) over the warp winners, post the record
                 const PWin* q = &sh.pw[lane & (kTW - 1)];
                 const int ww = warp_argmin(lane < kTW && q->off >= 0, q->rc, q->off);
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // be gathered without another round trip (otherwise wait_done() below polls)
             done_ok = (int)(ld_vol_u32(P.done + (size_t)(NP + tid - 128) * 32) - (unsigned)(k - 1)) >= 0;
         done_ok = __syncthreads_and(done_ok);
-        if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+        if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
         if (pricer && k > 1 && done_seen < k - 1 && done_ok) done_seen = k - 1;
         int win_rec = -1;                                 // round-0 record that holds the entering arc (every thread decodes it itself)
         {
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             win_rec = warp_argmin(v, mk64(sh.rec[pl][5].x, sh.rec[pl][5].y), sh.rec[pl][4].z);
             if (win_rec >= 0) { have_win = true; search_end = B < S ? B : S; }
         }
-        if (!have_win) {
+        if (!have_win) [[unlikely]] {
             if (pricer) {
                 // ---- later rounds, straight from global memory (every update visible first): in round r each pricer prices M
                 // consecutive blocks (M = 1, 2, 4, ... while NP*M <= 16), NP*M blocks per exchange; the lowest block with a negative reduced
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     for (int p = 0; p < NP; ++p) if (sh.rec[p][0].x >= 0) { found_blk = sh.rec[p][5].z; if (tid == 0) sh.win = unpack_pwin(sh.rec[p]); break; }
                     next_blk += (long long)NP * M;
                 }
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (found_blk >= 0) {
                     long long e = ((long long)found_blk + 1) * B; if (e > S) e = S;
                     search_end = (int)e; have_win = true;
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     sh.rec[0][tid] = v;
                 }
                 __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 have_win = sh.rec[0][0].x >= 0;
                 if (have_win && tid == 0) sh.win = unpack_pwin(sh.rec[0]);
             }
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // path) and BEFORE any owner applies update k: owners wait for GATHERED(k+1) below.  Update k is replayed at pricing.
             int s_lo, s_hi;
             const bool fits = share(B, s_lo, s_hi);
-            if (fits && !(spec_cursor == next_arc && spec_B == B)) {     // not what was predicted: drain and start over
+            if (fits && !(spec_cursor == next_arc && spec_B == B)) [[unlikely]] {     // not what was predicted: drain and start over
                 cp_async_wait_all();
                 stage_static_begin(next_arc, s_lo, s_hi, stv);
             }
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         if (w1 >= 0) m1 = sh.cl[w1];
                         if (w2 >= 0) m2 = sh.cl[w2];
                     }
-                } else {
+                } else [[unlikely]] {
                     // rare: many cycle nodes in one slice - recompute the candidates and reduce over the whole CTA
                     Cand b1 = cand_none(), b2 = cand_none();
                     for (int j = tid; j < cntn; j += kTT) {
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (l2 >= 0 && lane == l2) sh.wc[1][warp] = b2;
             }
             __syncthreads();
-            if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
             Cand w1 = cand_none(), w2 = cand_none();
             for (int w = 0; w < nw; ++w) {
                 const Cand t1 = sh.wc[0][w], t2 = sh.wc[1][w];
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         st_in[kx] = w[0].x; st_z[kx] = w[0].y; st_pd[kx] = w[0].z; st_fl[kx] = mk64(w[1].x, w[1].y); st_up[kx] = w[1].z;
                     }
                     __syncthreads();
-                    if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 }
                 TICK(t_stem);
             }
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 // hop 3: everything this CTA wrote for pivot k is visible before DONE(k)
                 PROBE(13);
                 __syncthreads();
-                if (sh.abort) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 if (tid == kTT - 32) { __threadfence(); st_vol_u32(P.done + (size_t)cta * 32, (unsigned)k); }   // not a thread that polls ENTER next
                 PROBE(14);
             }
