@@ -87,7 +87,7 @@ struct mcf_handle {
     int supply_type_solved = 0;
     // team engine (mcf_team.cu)
     DevBuf<mcf::NodeRec> d_node;
-    DevBuf<int4> d_mail;                                              // enter | cyc | stemhdr | stemseg
+    DevBuf<int4> d_mail;                                              // ent0 | prc | late | cyc | stemseg
     DevBuf<unsigned> d_done;
     DevBuf<long long> d_piout;
     std::vector<mcf::NodeRec> h_node;
@@ -358,9 +358,9 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     int rep_ent = 1, rep_cyc = 1;
     mcfk_team_replicas(&rep_ent, &rep_cyc);
     const size_t w_ent = (size_t)2 * rep_ent * pricers * mcf::kMailWords, w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords;
-    const size_t w_cyc = (size_t)2 * rep_cyc * team * mcf::kMailWords, w_hdr = (size_t)2 * team * mcf::kMailWords;
+    const size_t w_cyc = (size_t)2 * rep_cyc * team * mcf::kMailWords;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
-    const size_t seg_off = (w_ent + w_pr + w_late + w_cyc + w_hdr + 7) & ~(size_t)7;
+    const size_t seg_off = (w_ent + w_pr + w_late + w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
     for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = u == n ? 0 : 1; }
@@ -382,7 +382,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
     P->node = h->d_node.p; P->in_g = d_in_g; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
     P->ent0 = h->d_mail.p; P->prc = P->ent0 + w_ent; P->late = P->prc + w_pr; P->cyc = P->late + w_late;
-    P->stemhdr = P->cyc + w_cyc; P->stemseg = h->d_mail.p + seg_off;
+    P->stemseg = h->d_mail.p + seg_off;
     P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
     return MCF_OK;
 }

@@ -127,7 +127,6 @@ struct TeamParams {
     int4* late;                                          // [2][kMailWords]           pricer 0 -> all: result of a multi-block search
     int4* prc;                                           // [2][pricers][kMailWords]  pricer -> pricers: later rounds of a search
     int4* cyc;                                           // [2][team][kMailWords]     owner -> all
-    int4* stemhdr;                                       // [2][team][kMailWords]     owner -> all (stem exchange)
     int4* stemseg;                                       // [2][n+1][2]               stem entries, owner o at its slice offset
     unsigned int* done;                                  // [team + pricers][32]      owner -> pricers (DONE), pricer -> owners (GATHERED)
     Ctl* ctl;
