@@ -21,7 +21,7 @@ namespace MinCostFlow.Core.Cuda
     [StructLayout(LayoutKind.Sequential)]
     public struct McfOptions
     {
-        public int SupplyType, PivotRule, AutoConfiguration, OptimizedPivot, Device, MaxCtas, LookaheadBlocks, Engine;
+        public int SupplyType, PivotRule, AutoConfiguration, OptimizedPivot, Device, MaxCtas, LookaheadBlocks, Engine, SimdWidth, Reserved0;
         public long StopAfterPivots;
         public double BarrierTimeoutSeconds;
         public McfOptimizationConfig Config;

@@ -80,12 +80,19 @@ typedef struct mcf_options {
     int32_t supply_type;            /* SetSupplyType, NetworkSimplex.cs:197; default MCF_GEQ (:38) */
     int32_t pivot_rule;             /* SetPivotRule, NetworkSimplex.cs:206; default MCF_BLOCK_SEARCH (:77) */
     int32_t auto_configuration;     /* SetAutoConfiguration, NetworkSimplex.cs:567; default 1 (:90) */
-    int32_t optimized_pivot;        /* EnableOptimizedPivot, NetworkSimplex.cs:532.  First/Best Eligible: same pivots as
-                                       the managed rules.  Block Search: not supported yet -> MCF_ERR_INVALID_ARGUMENT */
+    int32_t optimized_pivot;        /* EnableOptimizedPivot, NetworkSimplex.cs:532: the rules of Internal/BlockSearchPivotOptimized.cs.
+                                       First/Best Eligible: same pivots as the managed rules.  Block Search: its own cursor
+                                       and wrap rules (:39-110), see simd_width */
     int32_t device;                 /* CUDA device ordinal */
     int32_t max_ctas;               /* 0 = one CTA per SM (cooperative-launch limit) */
     int32_t lookahead_blocks;       /* flat engine: blocks priced in the first pricing round (0 = 2); team engine: pricing CTAs (0 = auto) */
     int32_t engine;                 /* 0 = automatic; 1 = flat engine (mcf_kernels.cu); 2 = team engine (mcf_team.cu, Block Search) */
+    int32_t simd_width;             /* optimized Block Search only: Vector<long>.Count of the host whose pivot sequence is to be
+                                       reproduced (BlockSearchPivotOptimized.cs:74, :119): 4 = x64 AVX2 (default), 2 = SSE2 / NEON,
+                                       0 = Vector.IsHardwareAccelerated false.  With a non-zero width the reference's scalar loop
+                                       resumes after the vector loop's early return with its block counter at 0 and scans the
+                                       rest of the range; the engine reproduces exactly that */
+    int32_t reserved0;
     int64_t stop_after_pivots;      /* >0: stop after this many pivots with Status = NotSolved (bounded samples) */
     double barrier_timeout_s;       /* 0 = default 10 s */
     mcf_optimization_config config; /* SetOptimizationConfig, NetworkSimplex.cs:557-561 (used when auto_configuration == 0) */
@@ -98,7 +105,7 @@ typedef struct mcf_metrics {
     int32_t initial_block_size;         /* InitialBlockSize */
     int32_t final_block_size;           /* FinalBlockSize */
     int32_t baseline_iterations;        /* BaselineIterations = (int)(sqrt(S) * n * 0.5), NetworkSimplex.cs:276 */
-    int32_t pricing_kind;               /* 0 First, 1 Best, 2 Block, 3 cached Block (NetworkSimplex.cs:879-885) */
+    int32_t pricing_kind;               /* 0 First, 1 Best, 2 Block, 3 cached Block (NetworkSimplex.cs:879-885), 4 optimized Block (:851-856) */
     double average_arcs_checked_per_pivot;
     double iteration_ratio;
     double pivot_search_time_us;        /* PivotSearchTimeMicros  (device time in phase A) */

@@ -512,7 +512,7 @@ void mcf_default_options(mcf_options* o)
 {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));
-    o->supply_type = MCF_GEQ; o->pivot_rule = MCF_BLOCK_SEARCH; o->auto_configuration = 1; o->optimized_pivot = 0;
+    o->supply_type = MCF_GEQ; o->pivot_rule = MCF_BLOCK_SEARCH; o->auto_configuration = 1; o->optimized_pivot = 0; o->simd_width = 4;
     o->device = 0; o->max_ctas = 0; o->lookahead_blocks = 0; o->engine = 0; o->stop_after_pivots = 0; o->barrier_timeout_s = 0;
     default_config(&o->config);
 }
@@ -574,8 +574,7 @@ int mcf_set_options(mcf_handle* h, const mcf_options* opt)
     if (opt->supply_type != MCF_GEQ && opt->supply_type != MCF_LEQ) return fail(h, MCF_ERR_INVALID_ARGUMENT, "unknown supply type %d", opt->supply_type);
     if (opt->pivot_rule < MCF_FIRST_ELIGIBLE || opt->pivot_rule > MCF_BLOCK_SEARCH)
         return fail(h, MCF_ERR_INVALID_ARGUMENT, "pivot rule %d not implemented yet", opt->pivot_rule);   // NS.cs:884
-    if (opt->optimized_pivot && opt->pivot_rule == MCF_BLOCK_SEARCH)
-        return fail(h, MCF_ERR_INVALID_ARGUMENT, "optimized Block Search pivot (BlockSearchPivotOptimized.cs) is not supported by the CUDA engine yet");
+    if (opt->simd_width < 0 || opt->simd_width > 64) return fail(h, MCF_ERR_INVALID_ARGUMENT, "simd_width %d out of range", opt->simd_width);
     h->opt = *opt;
     return MCF_OK;
 }
@@ -619,8 +618,12 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     // CreatePivotRuleFinder, NS.cs:847-886 (+ BlockSearchPivot ctor :1304-1337)
     int kind = h->opt.pivot_rule;
     if (!h->opt.optimized_pivot && h->opt.pivot_rule == MCF_BLOCK_SEARCH && (cfg.flags & MCF_FLAG_REDUCED_COST_CACHING)) kind = mcf::PK_BLOCK_CACHED;
+    if (h->opt.optimized_pivot && h->opt.pivot_rule == MCF_BLOCK_SEARCH) kind = mcf::PK_BLOCK_OPT;          // NS.cs:851-856
     int block = 0, dyn_min = 0;
-    if (kind == mcf::PK_BLOCK || kind == mcf::PK_BLOCK_CACHED) {
+    if (kind == mcf::PK_BLOCK_OPT) {
+        block = std::max((int)std::sqrt((double)S), 10);                                              // BlockSearchPivotOptimized.cs:27-28 (MIN_BLOCK_SIZE, NS.cs:100)
+        cfg.flags &= ~MCF_FLAG_ADAPTIVE_BLOCK_SIZE;                                                   // the optimized rule never adapts
+    } else if (kind == mcf::PK_BLOCK || kind == mcf::PK_BLOCK_CACHED) {
         const int base = (int)std::sqrt((double)S);
         const int r = (int)(base * cfg.min_block_size_ratio);
         dyn_min = cfg.min_block_size > r ? cfg.min_block_size : r;
@@ -680,6 +683,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     P.low_thr = cfg.low_hit_rate_threshold; P.high_thr = cfg.high_hit_rate_threshold;
     P.shrink = cfg.block_size_shrink_factor; P.grow = cfg.block_size_growth_factor;
     P.lookahead0 = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : 2;
+    P.simd_width = h->opt.simd_width;
     P.max_iterations = std::max<int64_t>(1000000LL, (int64_t)n * m);                                  // NS.cs:280
     P.stop_after = h->opt.stop_after_pivots;
     const double tmo = h->opt.barrier_timeout_s > 0 ? h->opt.barrier_timeout_s : 10.0;
@@ -716,6 +720,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
     if (kind == mcf::PK_BEST) M.arcs_priced = ctl.pricing_rounds * (int64_t)S;
     else if (kind == mcf::PK_FIRST) M.arcs_priced = 0;       // not tracked for First Eligible
+    else if (kind == mcf::PK_BLOCK_OPT) { M.arcs_priced = ctl.arcs_priced_opt; M.final_block_size = 0; M.average_arcs_checked_per_pivot = 0; }
     else M.arcs_priced = ctl.arcs_checked;
     M.pricing_bytes = 16 * M.arcs_priced; M.engine = 1;
     h->total_cost = ctl.total_cost; h->d_pi_final = h->d_pi.p; h->supply_type_solved = h->opt.supply_type;

@@ -30,8 +30,9 @@ enum : int {
     ST_ERR_NEEDS_WIDE = 104             // team engine, narrow mode: a tree-arc flow left the int32 range (host re-runs wide)
 };
 
-// pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599)
-enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3 };
+// pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599; 4 = BlockSearchPivotOptimized,
+// Internal/BlockSearchPivotOptimized.cs:39-157)
+enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3, PK_BLOCK_OPT = 4 };
 
 struct __align__(16) PriceRec {         // one pricing candidate (per CTA, per round)
     long long c;                        // reduced cost (negative when valid, 0 = none)
@@ -66,6 +67,7 @@ struct Ctl {                            // control block in global memory (zeroe
     long long stem_exchanges;                                     // team engine: pivots that needed the stem exchange
     unsigned long long clk_total;                                 // team engine: clock64 ticks over the loop (phase accumulators are ticks)
     unsigned long long clk[16];                                   // team engine: sub-phase tick accumulators (0-7 pricing CTA, 8-15 owner CTA 1)
+    long long arcs_priced_opt;                                    // flat engine, PK_BLOCK_OPT: arcs priced (the reference keeps no counter there)
 };
 
 struct Params {
@@ -89,6 +91,7 @@ struct Params {
     int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
     double low_thr, high_thr, shrink, grow;
     int lookahead0;                     // groups priced in the first round of a search
+    int simd_width;                     // PK_BLOCK_OPT: Vector<long>.Count of the host the reference would run on (0 = scalar path)
     long long max_iterations;           // NS.cs:280
     long long stop_after;               // >0: stop after this many pivots (bounded samples / tests)
     unsigned long long barrier_timeout_cycles;

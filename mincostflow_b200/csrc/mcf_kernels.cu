@@ -172,6 +172,79 @@ __device__ __forceinline__ void sweep_quads(const Params& P, int first, int stri
     }
 }
 
+
+// Grid-wide arg-min of the reduced cost over the arcs [xa, xb): strictly below `bound`, lowest arc id among ties.  This is
+// the Best Eligible scan (NS.cs:1649-1658, bound 0 over [0, S)) and the "rest of the range" scan that
+// BlockSearchPivotOptimized falls into after its vector loop returned (BlockSearchPivotOptimized.cs:82-107).
+// Returns 1 and replaces sh.rec when an arc was found, 0 when none, -1 on a barrier time-out.
+__device__ int grid_best_in_range(const Params& P, Shared& sh, int xa, int xb, long long bound, int& price_buf,
+                                  unsigned long long& bar_target)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, cta = blockIdx.x;
+    Key best; best.a = bound; best.b = INT_MAX; best.idx = -1;
+    const int qa = (xa + 3) >> 2, qb = xb >> 2;
+    if (qa < qb) {
+        sweep_quads(P, qa + cta * kThreads + tid, G * kThreads, qb, best);
+        if (cta == 0 && tid < 8) {                  // the unaligned ends: [xa, 4 qa) and [4 qb, xb), at most 3 arcs each
+            const int e = tid < 4 ? xa + tid : (qb << 2) + tid - 4, lim = tid < 4 ? qa << 2 : xb;
+            if (e < lim) {
+                const long long r = reduced_cost(P, e);
+                if (r < best.a || (r == best.a && best.b != INT_MAX && e < best.b)) { best.a = r; best.b = e; }
+            }
+        }
+    } else {
+        for (int e = xa + cta * kThreads + tid; e < xb; e += G * kThreads) {
+            const long long r = reduced_cost(P, e);
+            if (r < best.a) { best.a = r; best.b = e; }
+        }
+    }
+    best.idx = tid;
+    best = block_min(best, sh.red[0]);
+    if (best.a < bound) { if (best.idx == tid) publish_candidate(P, price_buf, best.a, best.b, 0); }
+    else if (tid == 0) { P.part[(size_t)price_buf * G + cta].c = 0; P.part[(size_t)price_buf * G + cta].arc = INT_MAX; }
+    if (!grid_barrier(P, sh, bar_target)) return -1;
+    if (warp == 0) {
+        Key k = key_none(); k.a = bound;
+        for (int j = lane; j < G; j += 32) {
+            Key t; t.a = __ldcg(&P.part[(size_t)price_buf * G + j].c); t.b = __ldcg(&P.part[(size_t)price_buf * G + j].arc); t.idx = j;
+            if (t.a < bound && key_less(t, k)) k = t;
+        }
+        k = warp_min(k);
+        if (lane == 0) {
+            sh.found = k.a < bound ? k.idx : -1;
+            if (k.a < bound) {
+                const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + k.idx]);
+                int4* d = reinterpret_cast<int4*>(&sh.rec);
+                d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+            }
+        }
+    }
+    __syncthreads();
+    price_buf ^= 1;
+    return sh.found >= 0 ? 1 : 0;
+}
+
+// BlockSearchPivotOptimized.FindEnteringArc scans [next_arc, S) and then [0, next_arc) with ONE running block counter
+// (BlockSearchPivotOptimized.cs:48-55, `ref cnt`).  In scan offsets o = 0 .. S-1 from next_arc, a search is a list of
+// pieces: the blocks [kB, (k+1)B), with the block that contains the end of the first range (offset L1 = S - next_arc) cut
+// in two there.  A piece either ends where the counter reaches 0 (`--cnt == 0`, :98) or at the end of a range.
+struct OptPiece { int lo, hi; bool block_end; };
+__device__ __forceinline__ OptPiece opt_piece(long long p, int S, int B, int L1)
+{
+    const bool split = L1 < S && (L1 % B) != 0;
+    const int kc = L1 / B;
+    long long k = p;
+    bool first_half = false, second_half = false;
+    if (split) { if (p == kc) first_half = true; else if (p > kc) { k = p - 1; second_half = p == kc + 1; } }
+    long long lo = k * B, hi = lo + B;
+    OptPiece r; r.block_end = true;
+    if (hi > S) { hi = S; r.block_end = false; }
+    if (first_half) { hi = L1; r.block_end = false; }
+    if (second_half) lo = L1;
+    r.lo = (int)lo; r.hi = (int)hi;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 
 __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
@@ -188,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
     // replicated (uniform) solver state
     int next_arc = 0, B = P.block_size, cons_low = 0, cons_high = 0;
     long long iterations = 0, arcs_checked = 0, degenerate = 0, cycle_nodes = 0, moved_nodes = 0;
-    long long max_cycle = 0, max_stem = 0, rounds_total = 0;
+    long long max_cycle = 0, max_stem = 0, rounds_total = 0, arcs_priced_opt = 0;
     int price_buf = 0;                 // parity of the pricing round (double-buffers part[])
     int cache_dirty = 1;               // _reducedCostsDirty, NS.cs:65
     int status = ST_NOT_SOLVED;
@@ -331,39 +404,90 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
                 L = L * 2 < G ? L * 2 : G;
             }
             if (status != ST_NOT_SOLVED) break;
-        } else {  // PK_BEST: coalesced 128-bit sweep over all S arcs, lowest arc id wins ties (NS.cs:1649-1658)
-            Key best; best.a = 0; best.b = INT_MAX; best.idx = -1;
-            const int nquad = S >> 2;
-            sweep_quads(P, cta * kThreads + tid, G * kThreads, nquad, best);
-            for (int e = (nquad << 2) + cta * kThreads + tid; e < S; e += G * kThreads) {
-                const long long r = reduced_cost(P, e);
-                if (r < best.a) { best.a = r; best.b = e; }
-            }
-            best.idx = tid;
-            best = block_min(best, sh.red[0]);
-            if (best.a < 0) { if (best.idx == tid) publish_candidate(P, price_buf, best.a, best.b, 0); }
-            else if (tid == 0) { P.part[(size_t)price_buf * G + cta].c = 0; P.part[(size_t)price_buf * G + cta].arc = INT_MAX; }
-            if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            rounds_total++;
-            if (warp == 0) {
-                Key k = key_none(); k.a = 0;
-                for (int j = lane; j < G; j += 32) {
-                    Key t; t.a = __ldcg(&P.part[(size_t)price_buf * G + j].c); t.b = __ldcg(&P.part[(size_t)price_buf * G + j].arc); t.idx = j;
-                    if (t.a < 0 && key_less(t, k)) k = t;
-                }
-                k = warp_min(k);
-                if (lane == 0) {
-                    sh.found = k.a < 0 ? k.idx : -1;
+        } else if (P.kind == PK_BLOCK_OPT) {
+            // BlockSearchPivotOptimized.cs:39-157.  next_arc may be S here (`return e + 1` / `return e` at a range end).
+            const int L1 = S - next_arc;
+            const long long npieces = (S + (long long)B - 1) / B + ((L1 < S && (L1 % B) != 0) ? 1 : 0);
+            long long pieces_done = 0;
+            int L = P.lookahead0;
+            for (;;) {
+                const int nact = L < G ? L : G;
+                if (cta < nact && pieces_done + cta < npieces) {
+                    const OptPiece pc = opt_piece(pieces_done + cta, S, B, L1);
+                    long long bestc = 0; int bestoff = INT_MAX;
+                    for (int off = pc.lo + tid; off < pc.hi; off += kThreads) {
+                        int idx = next_arc + off; if (idx >= S) idx -= S;
+                        const long long c = reduced_cost(P, idx);
+                        if (c < bestc) { bestc = c; bestoff = off; }
+                    }
+                    Key k; k.a = bestc; k.b = bestoff; k.idx = tid;
+                    k = block_min(k, sh.red[0]);
                     if (k.a < 0) {
-                        const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + k.idx]);
-                        int4* d = reinterpret_cast<int4*>(&sh.rec);
-                        d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+                        if (k.idx == tid) { int idx = next_arc + k.b; if (idx >= S) idx -= S; publish_candidate(P, price_buf, k.a, idx, k.b); }
+                    } else if (tid == 0) {
+                        P.part[(size_t)price_buf * G + cta].c = 0;
+                    }
+                } else if (cta < nact && tid == 0) {
+                    P.part[(size_t)price_buf * G + cta].c = 0;
+                }
+                if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                rounds_total++;
+                if (warp == 0) {                    // first piece in scan order with a negative minimum
+                    int win = -1;
+                    for (int j0 = 0; j0 < nact && win < 0; j0 += 32) {
+                        const int j = j0 + lane;
+                        const long long c = j < nact ? __ldcg(&P.part[(size_t)price_buf * G + j].c) : 0;
+                        const unsigned mask = __ballot_sync(0xffffffffu, c < 0);
+                        if (mask) win = j0 + __ffs(mask) - 1;
+                    }
+                    if (lane == 0) {
+                        sh.found = win;
+                        if (win >= 0) {
+                            const int4* q = reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G + win]);
+                            int4* d = reinterpret_cast<int4*>(&sh.rec);
+                            d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
+                        }
                     }
                 }
+                __syncthreads();
+                price_buf ^= 1;
+                const int win = sh.found;
+                if (win >= 0) {
+                    const OptPiece pc = opt_piece(pieces_done + win, S, B, L1);
+                    const bool r2 = pc.lo >= L1;                               // the piece lies in the wrapped range [0, next_arc)
+                    const int rs = r2 ? L1 : 0, rlen = r2 ? next_arc : L1;     // range start (as an offset) and length
+                    const int V = P.simd_width;
+                    arcs_this = pc.hi;
+                    int nxt = r2 ? next_arc : S;                               // `return e` at the end of the range (:109)
+                    if (pc.block_end) {
+                        const int T = pc.hi - 1 - rs;                          // position in the range where `--cnt == 0` fired
+                        if (V > 0 && rlen >= 2 * V && T < (rlen / V) * V) {
+                            // fired inside ProcessArcRangeSIMD (:143-151): it returns with cnt == 0, the scalar loop of
+                            // ProcessArcRange then runs to the end of the range and can never stop (`--cnt` is negative)
+                            const int xa = r2 ? T + 1 : next_arc + pc.hi, xb = r2 ? next_arc : S;
+                            if (xa < xb) {
+                                const int r = grid_best_in_range(P, sh, xa, xb, sh.rec.c, price_buf, bar_target);
+                                if (r < 0) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                                rounds_total++;
+                                arcs_this += xb - xa;
+                            }
+                        } else nxt = (r2 ? 0 : next_arc) + T + 1;              // `return e + 1` (:100)
+                    }
+                    next_arc = nxt;
+                    found = true;
+                    break;
+                }
+                pieces_done += nact;
+                if (pieces_done >= npieces) { arcs_this = S; break; }
+                L = L * 2 < G ? L * 2 : G;
             }
-            __syncthreads();
-            price_buf ^= 1;
-            found = sh.found >= 0;
+            if (status != ST_NOT_SOLVED) break;
+            arcs_priced_opt += arcs_this;
+        } else {  // PK_BEST: coalesced 128-bit sweep over all S arcs, lowest arc id wins ties (NS.cs:1649-1658)
+            const int r = grid_best_in_range(P, sh, 0, S, 0, price_buf, bar_target);
+            if (r < 0) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            rounds_total++;
+            found = r > 0;
         }
         if (cta == 0 && tid == 0) { const unsigned long long t = globaltimer_ns(); t_price += t - t_mark; t_mark = t; }
         if (!found) { status = ST_OPTIMAL; break; }      // feasibility is decided in the epilogue
@@ -565,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
     }
     if (cta == 0 && tid == 0) {
         Ctl* c = P.ctl;
-        c->status = status; c->iterations = iterations; c->arcs_checked = arcs_checked; c->final_block_size = B;
+        c->status = status; c->iterations = iterations; c->arcs_checked = arcs_checked; c->final_block_size = B; c->arcs_priced_opt = arcs_priced_opt;
         c->degenerate = degenerate; c->cycle_nodes = cycle_nodes; c->moved_nodes = moved_nodes;
         c->max_cycle = max_cycle; c->max_stem = max_stem; c->pricing_rounds = rounds_total;
         c->ns_price = t_price; c->ns_cycle = t_cycle; c->ns_update = t_update; c->ns_total = globaltimer_ns() - t_begin;

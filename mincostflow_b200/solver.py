@@ -78,7 +78,8 @@ class _CConfig(C.Structure):
 class _COptions(C.Structure):
     _fields_ = [("supply_type", C.c_int32), ("pivot_rule", C.c_int32), ("auto_configuration", C.c_int32),
                 ("optimized_pivot", C.c_int32), ("device", C.c_int32), ("max_ctas", C.c_int32),
-                ("lookahead_blocks", C.c_int32), ("engine", C.c_int32), ("stop_after_pivots", C.c_int64),
+                ("lookahead_blocks", C.c_int32), ("engine", C.c_int32), ("simd_width", C.c_int32), ("reserved0", C.c_int32),
+                ("stop_after_pivots", C.c_int64),
                 ("barrier_timeout_s", C.c_double), ("config", _CConfig)]
 
 
@@ -327,8 +328,11 @@ class NetworkSimplex:
         self._opt.pivot_rule = int(rule)
         return self
 
-    def EnableOptimizedPivot(self, enable=True):
+    def EnableOptimizedPivot(self, enable=True, simd_width=None):
+        """NetworkSimplex.cs:532.  simd_width = Vector<long>.Count of the host whose pivot sequence the optimized Block Search
+        is to reproduce (BlockSearchPivotOptimized.cs:74): 4 on x64 AVX2 (default), 2 on SSE2 / NEON, 0 = not accelerated."""
         self._opt.optimized_pivot = int(bool(enable))
+        if simd_width is not None: self._opt.simd_width = int(simd_width)
 
     def SetMemoryPool(self, pool):          # stored but never read by the reference (NetworkSimplex.cs:541-544)
         pass

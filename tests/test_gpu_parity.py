@@ -28,7 +28,7 @@ def _oracle_cfg(cfg: mcf.OptimizationConfig):
     return c
 
 
-def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, optimized=False, expect_cost=None, engine=None):
+def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, optimized=False, expect_cost=None, engine=None, simd_width=4):
     """Solve on the GPU and on the oracle; everything observable must be identical."""
     ns = mcf.NetworkSimplex.from_problem(p)
     ns.SetPivotRule(rule).SetSupplyType(supply_type)
@@ -37,9 +37,9 @@ def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, opt
     if cfg is not None:
         ns.SetOptimizationConfig(cfg)
     if optimized:
-        ns.EnableOptimizedPivot(True)
+        ns.EnableOptimizedPivot(True, simd_width=simd_width)
     st = ns.Solve()
-    r, rflow, rpi, _, _ = oracle.solve(p, pivot_rule=int(rule), supply_type=supply_type, optimized_pivot=optimized,
+    r, rflow, rpi, _, _ = oracle.solve(p, pivot_rule=int(rule), supply_type=supply_type, optimized_pivot=optimized, simd_width=simd_width,
                                        config=None if cfg is None else _oracle_cfg(cfg))
     M = ns.GetMetrics()
     tag = (p.name, int(rule), supply_type, optimized)
@@ -155,8 +155,29 @@ def test_small_fixtures_all_rules_and_optimized_pivot(golden, load_fixture, rule
             continue
         p = load_fixture(name)
         check_parity(p, rule=rule, expect_cost=e.get("objective"))
-        if rule != mcf.PivotRule.BlockSearch:                       # optimized Block Search is refused by the engine
-            check_parity(p, rule=rule, optimized=True, expect_cost=e.get("objective"))
+        check_parity(p, rule=rule, optimized=True, expect_cost=e.get("objective"))
+
+
+def test_optimized_block_search_pivot(golden, load_fixture):
+    """BlockSearchPivotOptimized.cs:39-157 (`EnableOptimizedPivot` + Block Search): own cursor rule (`_nextArc = e + 1`), one block
+    counter across the wrap, and - when Vector<long> is hardware accelerated - the scalar loop resuming after the vector loop's
+    early return with the counter at 0, i.e. scanning the rest of the range.  Every Vector<long>.Count a host can have."""
+    for name in ("circulation_1000_0_05", "netgen_8_08a", "netgen_8_10a", "grid_5x5", "transport_400x300"):
+        e = golden["fixtures"].get(name)
+        if e is None or not e.get("stored"):
+            continue
+        p = load_fixture(name)
+        for vw in (4, 0, 2, 8):
+            ns, r = check_parity(p, optimized=True, simd_width=vw, expect_cost=e.get("objective"))
+            assert ns.GetMetrics().pricing_kind == 4 and r.pivot_kind == 12
+    p = instances.netgen8(13)
+    for vw in (4, 0):
+        check_parity(p, optimized=True, simd_width=vw, cfg=mcf.OptimizationConfig(), expect_cost=golden["fixtures"]["netgen_8_13a"]["objective"])
+    # tiny instances: ranges shorter than two vectors take the scalar path even when accelerated (:74)
+    for case in golden["lemon_cases"][:6]:
+        q, stype, _, _ = lemon_case_problem(golden, case)
+        for vw in (4, 0):
+            check_parity(q, optimized=True, simd_width=vw, supply_type=stype)
 
 
 def test_published_pivot_counts_on_gpu(golden, load_fixture):
