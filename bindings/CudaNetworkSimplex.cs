@@ -37,6 +37,14 @@ namespace MinCostFlow.Core.Cuda
         [DllImport(Lib)] internal static extern int mcf_set_supply(IntPtr h, long* supply);
         [DllImport(Lib)] internal static extern int mcf_set_options(IntPtr h, ref McfOptions o);
         [DllImport(Lib)] internal static extern int mcf_solve(IntPtr h, out int status);
+        // Problems/Loaders: DimacsReader.cs:25-147, SolutionLoader.cs:69-214 (bulk, native)
+        [DllImport(Lib)] internal static extern int mcf_create_from_dimacs([MarshalAs(UnmanagedType.LPUTF8Str)] string path, out IntPtr handle);
+        [DllImport(Lib)] internal static extern int mcf_dimacs_open([MarshalAs(UnmanagedType.LPUTF8Str)] string path, out IntPtr dimacs);
+        [DllImport(Lib)] internal static extern int mcf_dimacs_dims(IntPtr dimacs, out int n, out int m);
+        [DllImport(Lib)] internal static extern int mcf_dimacs_copy(IntPtr dimacs, int* source, int* target, long* lower, long* upper, long* cost, long* supply);
+        [DllImport(Lib)] internal static extern void mcf_dimacs_close(IntPtr dimacs);
+        [DllImport(Lib)] internal static extern int mcf_write_solution(IntPtr h, [MarshalAs(UnmanagedType.LPUTF8Str)] string path, int format, int withPotentials);
+        [DllImport(Lib)] internal static extern IntPtr mcf_io_last_error();
         [DllImport(Lib)] internal static extern int mcf_get_flows(IntPtr h, long* outM);
         [DllImport(Lib)] internal static extern int mcf_get_potentials(IntPtr h, long* outN);
         [DllImport(Lib)] internal static extern int mcf_get_total_cost(IntPtr h, out long cost);
@@ -73,7 +81,12 @@ namespace MinCostFlow.Core.Cuda
         public CudaNetworkSimplex SetNodeSupply(Node node, long supply) { if (!_graph.IsValidNode(node)) throw new ArgumentException("Invalid node"); _supply[node.Id] = supply; return this; }
         public CudaNetworkSimplex SetSupplyType(SupplyType type) { _opt.SupplyType = (int)type; return this; }
         public CudaNetworkSimplex SetPivotRule(PivotRule rule) { _opt.PivotRule = (int)rule; return this; }
-        public void EnableOptimizedPivot(bool enable = true) => _opt.OptimizedPivot = enable ? 1 : 0;
+        public void EnableOptimizedPivot(bool enable = true)
+        {
+            _opt.OptimizedPivot = enable ? 1 : 0;
+            // BlockSearchPivotOptimized.cs:74, :119 - the managed rule's pivot sequence depends on the vector width of this host
+            _opt.SimdWidth = System.Numerics.Vector.IsHardwareAccelerated ? System.Numerics.Vector<long>.Count : 0;
+        }
         public void SetAutoConfiguration(bool enable) => _opt.AutoConfiguration = enable ? 1 : 0;
         public void SetOptimizationConfig(OptimizationConfig c)
         {

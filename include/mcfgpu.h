@@ -47,7 +47,9 @@ typedef enum mcf_error {
     MCF_ERR_RANGE = -6,                       /* |cost| does not fit int32, or too many arcs (m + 2n >= 2^30) */
     MCF_ERR_ENGINE_LIMIT = -7,                /* pivot cycle / stem longer than the in-kernel staging buffers */
     MCF_ERR_TIMEOUT = -8,                     /* a grid barrier timed out (kernel abandoned) */
-    MCF_ERR_NOT_SOLVED = -9                   /* metrics / results requested before mcf_solve */
+    MCF_ERR_NOT_SOLVED = -9,                  /* metrics / results requested before mcf_solve */
+    MCF_ERR_FORMAT = -10,                     /* malformed DIMACS text (FormatException in DimacsReader.cs); see mcf_io_last_error */
+    MCF_ERR_IO = -11                          /* file cannot be read / written */
 } mcf_error;
 
 /* Enum values are the reference's: SolverStatus.cs:7-34, PivotRule.cs:7-40, SupplyType.cs:7-17,
@@ -192,6 +194,38 @@ int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_o
  * slackness (:135-176), 8 dual feasibility of the supply form (:191-231), 16 objective != sum flow*cost (:234-262),
  * 32 dual objective != primal (:268-342); 0 = IsValid.  MCF_ERR_NOT_OPTIMAL unless Status == Optimal (:24-33). */
 int mcf_validate(mcf_handle* h, int32_t* failed_checks_out, int64_t* primal_objective_out, int64_t* dual_objective_out);
+
+/* ---- DIMACS bulk I/O: the step before and after the path (host code, mcf_io.cpp) -------------------------------------
+ * DimacsReader.ReadFromStream (src/MinCostFlow.Problems/Loaders/DimacsReader.cs:36-147) as one parallel pass over the
+ * text into flat arrays in arc-id order (= order of the `a` lines), replacing the reader + the per-element setter loop
+ * of Benchmarks/NetworkSimplexBenchmarks.cs:166-189.  Same grammar and errors: `p min N M` (:67-81), `n ID SUPPLY`
+ * (:83-93, 1-based ids, a later line overrides), `a FROM TO LOWER UPPER COST` (:95-109), `c` and unknown lines skipped,
+ * wrong token counts / non-numbers -> MCF_ERR_FORMAT with the reference's message.  Deviation: an arc count different
+ * from the `p` line is refused (the reference throws IndexOutOfRange or leaves arrays and graph of different sizes). */
+typedef struct mcf_dimacs mcf_dimacs;
+int mcf_dimacs_open(const char* path, mcf_dimacs** out);
+int mcf_dimacs_parse(const char* text, int64_t length, mcf_dimacs** out);
+int mcf_dimacs_dims(const mcf_dimacs* d, int32_t* n_out, int32_t* m_out);
+/* any pointer may be NULL; source/target/lower/upper/cost hold m entries, supply n */
+int mcf_dimacs_copy(const mcf_dimacs* d, int32_t* source, int32_t* target, int64_t* lower, int64_t* upper, int64_t* cost, int64_t* supply);
+void mcf_dimacs_close(mcf_dimacs* d);
+/* DimacsReader.ReadFromFile + new NetworkSimplex(graph) + SetArcBounds / SetArcCost / SetNodeSupply for every element */
+int mcf_create_from_dimacs(const char* path, mcf_handle** out);
+/* SolutionLoader.SaveToFile (Loaders/SolutionLoader.cs:186-214): `s COST`, one `f` line per non-zero flow, optional
+ * `p NODE POTENTIAL` lines.  format 0: `f ARC_ID FLOW` (0-based arc id, what SaveToFile writes); format 1: `f SRC DST FLOW`
+ * (1-based node ids, the form of the .sol fixtures under Resources/, :124-129).  MCF_ERR_NOT_OPTIMAL unless Optimal. */
+int mcf_write_solution(mcf_handle* h, const char* path, int32_t format, int32_t with_potentials);
+/* SolutionLoader.LoadFromStream (:69-173): objective (INT64_MIN = "not specified", :165-170) and the `f` lines: up to
+ * `capacity` of them into a_out / b_out / flow_out (arc id and -1, or 0-based source and target); *flow_lines_out = how many
+ * the file holds; *endpoint_form_out = 1 if any line had the SRC DST form.  Output pointers may be NULL. */
+int mcf_read_solution(const char* path, int64_t* cost_out, int32_t capacity, int32_t* a_out, int32_t* b_out, int64_t* flow_out,
+                      int32_t* flow_lines_out, int32_t* endpoint_form_out);
+/* message of the last failed I/O call on this thread */
+const char* mcf_io_last_error(void);
+
+/* number of nodes / arcs and the arc endpoints the handle was created with */
+int mcf_get_dims(mcf_handle* h, int32_t* n_out, int32_t* m_out);
+int mcf_get_endpoints(mcf_handle* h, int32_t* source_out, int32_t* target_out);
 
 const char* mcf_last_error(mcf_handle* h);
 

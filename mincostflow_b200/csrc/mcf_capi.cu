@@ -561,6 +561,22 @@ int mcf_set_arcs(mcf_handle* h, const int64_t* lower, const int64_t* upper, cons
     return MCF_OK;
 }
 
+int mcf_get_dims(mcf_handle* h, int32_t* n_out, int32_t* m_out)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    if (n_out) *n_out = h->n;
+    if (m_out) *m_out = h->m;
+    return MCF_OK;
+}
+
+int mcf_get_endpoints(mcf_handle* h, int32_t* source_out, int32_t* target_out)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    if (source_out && h->m > 0) std::memcpy(source_out, h->source.data(), (size_t)h->m * 4);
+    if (target_out && h->m > 0) std::memcpy(target_out, h->target.data(), (size_t)h->m * 4);
+    return MCF_OK;
+}
+
 int mcf_set_supply(mcf_handle* h, const int64_t* supply)
 {
     if (!h || (!supply && h->n > 0)) return MCF_ERR_INVALID_ARGUMENT;
