@@ -185,7 +185,9 @@ int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* de
 /* Roofline probe: uploads the handle's initial basis and runs the stand-alone Best Eligible pricing sweep
  * (one full pass over all S = m + n arcs, 16 B of arc data per arc) `reps` times, timing each launch with CUDA
  * events on the handle's stream.  ms_out[reps] receives the per-launch times, *entering_arc_out the arg-min arc
- * (lowest id among ties, -1 if none).  When flush_l2 != 0 a buffer larger than L2 is overwritten between launches. */
+ * (lowest id among ties, -1 if none).  flush_l2 != 0: a 256 MB buffer (L2 is 126 MB) is overwritten between launches; with
+ * flush_l2 == 1 a second 256 MB buffer is then read, so that the write-back of the first one's dirty lines does not fall into the
+ * timed launch (2 = overwrite only). */
 int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_out, int32_t* entering_arc_out,
                       int64_t* arcs_per_launch_out);
 

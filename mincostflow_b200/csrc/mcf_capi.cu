@@ -23,6 +23,7 @@
 extern "C" int mcfk_pivot_smem_bytes();
 extern "C" int mcfk_max_grid(int device, int* sm_count);
 extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t stream);
+extern "C" int mcfk_launch_l2_read(const void* buf, size_t bytes, long long* sink, int sms, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaStream_t stream);
 extern "C" size_t mcfk_team_smem_bytes(int slice, int wide);
@@ -888,12 +889,21 @@ int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_o
     if (rc != MCF_OK) return rc;
     mcf::Params P; fill_params(h, &P);
     P.kind = mcf::PK_BEST;
-    const size_t flush_bytes = 256u << 20;          // > 126 MB L2
-    if (flush_l2) CUDA_TRY(h, h->d_flush.ensure(flush_bytes));
+    // L2 flush between launches: overwrite a buffer larger than L2 (126 MB), then (flush_l2 == 1) read a second one, so that
+    // the kernel starts on a cold L2 without having to write the first buffer's dirty lines back inside the timed region
+    // (tools/micro/stream.cu, profiles/r01_micro_stream.txt: +4 us on a 151 MB read-only stream otherwise)
+    const size_t flush_bytes = 256u << 20;
+    if (flush_l2) { CUDA_TRY(h, h->d_flush.ensure(2 * flush_bytes)); CUDA_TRY(h, cudaMemsetAsync(h->d_flush.p + flush_bytes, 0x5a, flush_bytes, h->stream)); }
     cudaEvent_t ev0, ev1;
     CUDA_TRY(h, cudaEventCreate(&ev0)); CUDA_TRY(h, cudaEventCreate(&ev1));
     for (int r = 0; r < reps; ++r) {
-        if (flush_l2) CUDA_TRY(h, cudaMemsetAsync(h->d_flush.p, r & 0xff, flush_bytes, h->stream));
+        if (flush_l2) {
+            CUDA_TRY(h, cudaMemsetAsync(h->d_flush.p, r & 0xff, flush_bytes, h->stream));
+            if (flush_l2 == 1) {
+                const int frc = mcfk_launch_l2_read(h->d_flush.p + flush_bytes, flush_bytes, reinterpret_cast<long long*>(h->d_part.p), sms, h->stream);
+                if (frc != 0) return fail(h, MCF_ERR_CUDA, "flush launch failed: %s", cudaGetErrorString((cudaError_t)frc));
+            }
+        }
         CUDA_TRY(h, cudaEventRecord(ev0, h->stream));
         const int lrc = mcfk_launch_price_sweep(&P, h->d_part.p, grid, h->stream);
         if (lrc != 0) return fail(h, MCF_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString((cudaError_t)lrc));

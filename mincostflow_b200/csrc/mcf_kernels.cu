@@ -717,6 +717,18 @@ __global__ void __launch_bounds__(kThreads, 1) ns_price_sweep_kernel(const Param
 }
 
 
+// Read-only pass over a buffer larger than L2 (second half of the probe's L2 flush): evicts the dirty lines the preceding
+// memset left behind, so that their write-back is not charged to the kernel that is timed next.
+__global__ void __launch_bounds__(512) ns_l2_read_kernel(const int4* buf, size_t n4, long long* sink)
+{
+    long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 v = __ldcg(buf + i);
+        acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x7f5a5a5a5a5a5a5aLL) *sink = acc;      // never true for a memset pattern; keeps the loads alive
+}
+
 // ------------------------------------------------------------------------------------------------
 // SolutionValidator (Lemon/Validation/SolutionValidator.cs:20-342) as two streaming reductions over the arrays the solve
 // left in HBM: flow conservation (:55-100), bounds (:102-125), complementary slackness (:135-176), dual feasibility of the
@@ -801,6 +813,12 @@ extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaS
     const int grid = sms * 8;
     mcf::ns_validate_arcs_kernel<<<grid, 256, 0, stream>>>(*v);
     mcf::ns_validate_nodes_kernel<<<grid, 256, 0, stream>>>(*v);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mcfk_launch_l2_read(const void* buf, size_t bytes, long long* sink, int sms, cudaStream_t stream)
+{
+    mcf::ns_l2_read_kernel<<<sms * 4, 512, 0, stream>>>(reinterpret_cast<const int4*>(buf), bytes / 16, sink);
     return (int)cudaGetLastError();
 }
 

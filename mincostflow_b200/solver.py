@@ -439,7 +439,8 @@ class NetworkSimplex:
         return bad.value, primal.value, dual.value
 
     def pricing_probe(self, reps=5, flush_l2=True):
-        """Stand-alone Best Eligible sweep over all S arcs (mcf_pricing_probe).  Returns (ms per launch, arc, S)."""
+        """Stand-alone Best Eligible sweep over all S arcs (mcf_pricing_probe).  Returns (ms per launch, arc, S).
+        flush_l2: 0 none, 1 / True overwrite 256 MB then read 256 MB between launches, 2 overwrite only."""
         self._push()
         ms = np.zeros(reps, np.float32)
         arc = C.c_int32(-1); arcs = C.c_int64(0)
