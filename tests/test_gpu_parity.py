@@ -173,6 +173,8 @@ def test_optimized_block_search_pivot(golden, load_fixture):
     p = instances.netgen8(13)
     for vw in (4, 0):
         check_parity(p, optimized=True, simd_width=vw, cfg=mcf.OptimizationConfig(), expect_cost=golden["fixtures"]["netgen_8_13a"]["objective"])
+    # BASELINE config 2 size with the scalar semantics (a full-length Block Search with the optimized rule's cursor / wrap rules)
+    check_parity(instances.netgen8(16), optimized=True, simd_width=0, cfg=mcf.OptimizationConfig())
     # tiny instances: ranges shorter than two vectors take the scalar path even when accelerated (:74)
     for case in golden["lemon_cases"][:6]:
         q, stype, _, _ = lemon_case_problem(golden, case)
