@@ -142,7 +142,9 @@ __device__ __forceinline__ ArcQuad load_quad(const Params& P, int q)
 __device__ __forceinline__ void price_quad(const Params& P, const ArcQuad& a, int q, Key& best)
 {
     // arc lists are usually grouped by tail node: consecutive arcs share pi[source], one gather serves the run
-    const long long pt0 = __ldcg(P.pi + a.t.x), pt1 = __ldcg(P.pi + a.t.y), pt2 = __ldcg(P.pi + a.t.z), pt3 = __ldcg(P.pi + a.t.w);
+    // a basis arc (state 0) has reduced cost 0 whatever its potentials: its random target gather is skipped (n - 1 of the S arcs)
+    const long long pt0 = a.st.x ? __ldcg(P.pi + a.t.x) : 0, pt1 = a.st.y ? __ldcg(P.pi + a.t.y) : 0;
+    const long long pt2 = a.st.z ? __ldcg(P.pi + a.t.z) : 0, pt3 = a.st.w ? __ldcg(P.pi + a.t.w) : 0;
     const long long ps0 = __ldcg(P.pi + a.s.x);
     const long long ps1 = a.s.y == a.s.x ? ps0 : __ldcg(P.pi + a.s.y);
     const long long ps2 = a.s.z == a.s.y ? ps1 : __ldcg(P.pi + a.s.z);
