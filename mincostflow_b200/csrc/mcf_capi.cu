@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -98,6 +99,20 @@ struct mcf_handle {
 };
 
 namespace {
+
+// The persisting-L2 set-aside is a device-wide limit, and changing it waits for the kernels that are running on the device:
+// with several solves side by side (mcf_solve_batch_concurrent) a per-solve cudaDeviceSetLimit serialised them.  It is
+// therefore only ever raised, under a lock, and the batch entry point raises it once before its workers start.
+std::mutex g_persist_mu;
+size_t g_persist_limit[64] = {0};
+void ensure_persisting_l2(int device, size_t want)
+{
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_persist_mu);
+    if (g_persist_limit[device] >= want) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) g_persist_limit[device] = want;
+    else cudaGetLastError();
+}
 
 int fail(mcf_handle* h, int code, const char* fmt, ...)
 {
@@ -424,7 +439,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
         const size_t mirror_bytes = (size_t)(n + 1) * (sizeof(mcf::NodeRec) + 4);
         if (max_win > 0 && max_persist > 0) {
             const size_t want = std::min<size_t>(mirror_bytes + (1u << 20), (size_t)max_persist);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            ensure_persisting_l2(h->opt.device, want);
             cudaStreamAttrValue av{};
             av.accessPolicyWindow.base_ptr = h->d_node.p;
             av.accessPolicyWindow.num_bytes = std::min<size_t>(mirror_bytes, (size_t)max_win);
@@ -838,6 +853,16 @@ int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* de
     // the SMs (a 2^18-node instance needs 37 CTAs, four run side by side on 148 SMs).  The solves are independent - no kernel
     // ever waits for another one - so they may also simply run one after the other if the SMs are not free.
     const int lanes = n_devices * per_device;
+    if (per_device > 1) {                           // raise the persisting-L2 set-aside once, before any kernel runs (see ensure_persisting_l2)
+        int max_n = 0;
+        for (int i = 0; i < count; ++i) if (hs[i] && hs[i]->n > max_n) max_n = hs[i]->n;
+        for (int d = 0; d < n_devices; ++d) {
+            int max_persist = 0;
+            if (cudaSetDevice(devices[d]) != cudaSuccess || cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, devices[d]) != cudaSuccess) { cudaGetLastError(); continue; }
+            const size_t one = (size_t)(max_n + 1) * (sizeof(mcf::NodeRec) + 4) + (1u << 20);
+            ensure_persisting_l2(devices[d], std::min<size_t>(one * (size_t)per_device, (size_t)max_persist));
+        }
+    }
     std::vector<int> rcs(lanes, MCF_OK);
     std::vector<std::thread> workers;
     for (int w = 0; w < lanes; ++w) {
