@@ -6,7 +6,8 @@
 //                                                      :205-245 ComplementarySlackness_ValidatedCorrectly
 //   src/MinCostFlow.Tests/Lemon/OptimizationTests.cs:14-70       optimized pivot == baseline (status, cost, flows)
 // plus the reference's error behaviour (NetworkSimplex.cs:155-158, :418-421, :884) and the DIMACS path.
-// Usage: test_network_simplex [--no-device] [dimacs-dir]      exit code 0 = all passed.
+// Usage: test_network_simplex [--no-device] <dir with grid_5x5.min and netgen_8_08a.min>      exit code 0 = all passed.
+// (tests/test_cpp_mirror.py writes the directory: conftest.dimacs_dir)
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -176,7 +177,7 @@ static void DimacsPath(const std::string& dir)
 
 int main(int argc, char** argv)
 {
-    bool no_device = false; std::string dir = "tests/golden/dimacs";
+    bool no_device = false; std::string dir = ".";
     for (int i = 1; i < argc; ++i) { if (!std::strcmp(argv[i], "--no-device")) no_device = true; else dir = argv[i]; }
     if (no_device) {
         // no CPU fallback: without an sm_100 GPU the constructor must fail loudly (mcf_create -> MCF_ERR_NO_DEVICE)

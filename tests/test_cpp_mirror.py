@@ -5,29 +5,28 @@ import subprocess
 
 import pytest
 
-from conftest import GOLDEN_DIR, ROOT
+from conftest import ROOT
 import mincostflow_b200 as mcf
 
 EXE = os.path.join(ROOT, "tests", "cpp", "test_network_simplex")
-DIMACS_DIR = os.path.join(GOLDEN_DIR, "dimacs")
 
 
-def _run(*args):
+def _run(dimacs_dir, *args):
     if not os.path.exists(EXE):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mincostflow_b200", "csrc"), "all"])
-    return subprocess.run([EXE, *args, DIMACS_DIR], capture_output=True, text=True, timeout=600)
+    return subprocess.run([EXE, *args, dimacs_dir], capture_output=True, text=True, timeout=600)
 
 
-def test_cpp_mirror_builds_and_fails_loudly_without_a_device():
+def test_cpp_mirror_builds_and_fails_loudly_without_a_device(dimacs_dir):
     if mcf.device_count() > 0:
         pytest.skip("a GPU is present: covered by the gpu test")
-    r = _run("--no-device")
+    r = _run(dimacs_dir, "--no-device")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failed" in r.stdout
 
 
 @pytest.mark.gpu
-def test_reference_xunit_tests_in_cpp():
-    r = _run()
+def test_reference_xunit_tests_in_cpp(dimacs_dir):
+    r = _run(dimacs_dir)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failed" in r.stdout

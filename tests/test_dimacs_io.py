@@ -1,7 +1,7 @@
 """Native bulk DIMACS I/O (csrc/mcf_io.cpp through mincostflow_b200/dimacs.py): DimacsReader.ReadFromStream
-(Loaders/DimacsReader.cs:36-147) and SolutionLoader (Loaders/SolutionLoader.cs:60-214) semantics, pinned on the reference's
-own fixture files (tests/golden/dimacs/, copied by tools/make_golden_dimacs.py) and on the arrays tools/make_golden.py
-produced from the same files with the plain-Python reader."""
+(Loaders/DimacsReader.cs:36-147) and SolutionLoader (Loaders/SolutionLoader.cs:60-214) semantics, pinned on a byte-identical
+regeneration of the reference's netgen_8_08a.min and on the arrays tools/make_golden.py produced from the reference's fixture
+files with the plain-Python reader (conftest.dimacs_dir)."""
 import ctypes as C
 import glob
 import os
@@ -13,7 +13,6 @@ from conftest import GOLDEN_DIR
 import mincostflow_b200 as mcf
 from mincostflow_b200 import dimacs, instances
 
-DIMACS_DIR = os.path.join(GOLDEN_DIR, "dimacs")
 FIELDS = ("source", "target", "lower", "upper", "cost", "supply")
 
 
@@ -23,8 +22,8 @@ def _same(p, q):
         assert np.array_equal(getattr(p, a), getattr(q, a)), a
 
 
-def test_reference_fixture_files_parse_like_the_reference(load_fixture, golden):
-    files = sorted(glob.glob(os.path.join(DIMACS_DIR, "*.min")))
+def test_reference_fixture_files_parse_like_the_reference(load_fixture, golden, dimacs_dir):
+    files = sorted(glob.glob(os.path.join(dimacs_dir, "*.min")))
     assert len(files) >= 5
     for path in files:
         name = os.path.splitext(os.path.basename(path))[0]
@@ -33,7 +32,7 @@ def test_reference_fixture_files_parse_like_the_reference(load_fixture, golden):
         _same(p, instances.read_dimacs_min(path))
         sol = dimacs.load_solution(path[:-4] + ".sol")
         assert sol.OptimalCost == golden["fixtures"][name]["objective"]
-        assert sol.ArcFlowsByEndpoints and all(0 <= s < p.n and 0 <= t < p.n for s, t in sol.ArcFlowsByEndpoints)      # 1-based in the file
+        assert sol.ArcFlowsByEndpoints == {(0, 1): 1}                    # `f 1 2 1`: node ids are 1-based in the file
 
 
 def test_large_text_takes_the_parallel_path_and_keeps_arc_order():
@@ -44,7 +43,7 @@ def test_large_text_takes_the_parallel_path_and_keeps_arc_order():
     _same(dimacs.read_from_text(instances.write_dimacs_min(p, ["c x"] * 3)), p)
 
 
-def test_grammar_and_errors():
+def test_grammar_and_errors(dimacs_dir):
     ok = "c comment\n\nx unknown line type is skipped\np min 3 2\nn 1 5\nn 3 -5\nn 1 4\na 1 2 0 10 7\na 2 3 1 +9 -2\r\n"
     p = dimacs.read_from_text(ok)
     assert (p.n, p.m) == (3, 2) and p.supply.tolist() == [4, 0, -5]      # a later `n` line overrides (DimacsReader.cs:92)
@@ -60,7 +59,7 @@ def test_grammar_and_errors():
         with pytest.raises(dimacs.FormatException, match=msg):
             dimacs.read_from_text(bad)
     with pytest.raises(OSError):
-        dimacs.read_from_file(os.path.join(DIMACS_DIR, "does_not_exist.min"))
+        dimacs.read_from_file(os.path.join(dimacs_dir, "does_not_exist.min"))
 
 
 def test_solution_reader_forms(tmp_path):
@@ -74,12 +73,12 @@ def test_solution_reader_forms(tmp_path):
 
 
 @pytest.mark.gpu
-def test_create_from_dimacs_solve_and_write_solution(tmp_path, golden):
+def test_create_from_dimacs_solve_and_write_solution(tmp_path, golden, dimacs_dir):
     """mcf_create_from_dimacs (reader + graph + all setters in one native call) -> Solve -> SaveToFile -> LoadFromFile."""
     lib = mcf.load_library()
     dimacs._lib()
     for name in ("grid_5x5", "netgen_8_08a", "transport_2x3"):
-        path = os.path.join(DIMACS_DIR, name + ".min")
+        path = os.path.join(dimacs_dir, name + ".min")
         h = C.c_void_p()
         assert lib.mcf_create_from_dimacs(path.encode(), C.byref(h)) == 0
         st, cost = C.c_int32(), C.c_int64()
@@ -104,6 +103,6 @@ def test_create_from_dimacs_solve_and_write_solution(tmp_path, golden):
                 assert s.ArcFlows == {int(e): int(fl[e]) for e in np.nonzero(fl)[0]}
                 lines = open(out).read().splitlines()
                 assert lines[0] == f"s {ns.GetTotalCost()}" and sum(l.startswith("p ") for l in lines) == p.n
-    unsolved = mcf.NetworkSimplex.from_problem(dimacs.read_from_file(os.path.join(DIMACS_DIR, "grid_5x5.min")))
+    unsolved = mcf.NetworkSimplex.from_problem(dimacs.read_from_file(os.path.join(dimacs_dir, "grid_5x5.min")))
     with pytest.raises(mcf.InvalidOperationException):
         dimacs.save_solution(unsolved, str(tmp_path / "x.sol"))
