@@ -310,6 +310,13 @@ def run_ours(args):
                          "cycle_us_per_pivot": M.cycle_time_us / max(M.iterations, 1),
                          "update_us_per_pivot": M.tree_update_time_us / max(M.iterations, 1),
                          "arcs_priced_per_pivot": M.arcs_priced / max(M.iterations, 1),
+                         # in-kernel probes of the team engine (clock64 deltas of one pricing CTA and of the first owner CTA), us per pivot
+                         "pricer_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
+                             ("price_and_post_ENTER", 1), ("collect_ENTER", 2), ("stage_next_block_arcs", 3), ("wait_DONE", 6), ("finish_staging", 0),
+                             ("gather_node_records_post_GATHERED", 7), ("wait_and_gather_CYC", 4), ("decide", 5))} if M.engine == 2 else None,
+                         "owner_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
+                             ("wait_and_collect_ENTER", 9), ("scan_slice", 10), ("reduce_and_post_CYC", 11), ("gather_CYC_and_decide", 12),
+                             ("cycle_node_update", 15), ("relabel", 13), ("post_DONE", 14))} if M.engine == 2 else None,
                          "pricing_GBps_in_kernel": M.pricing_bytes / max(M.pivot_search_time_us, 1e-9) / 1e3},
     }
     # CPU baseline (oracle port) on a bounded sample + the GPU on the very same sample
