@@ -173,6 +173,12 @@ int mcf_get_arc_upper_bound(mcf_handle* h, int32_t arc, int64_t* out);
 
 int mcf_get_metrics(mcf_handle* h, mcf_metrics* out);             /* GetMetrics, NetworkSimplex.cs:584 */
 
+/* The result arrays of the last Optimal solve where the solve left them in HBM (flow[m] in arc-id order, potential[n] in
+ * node-id order, both int64) and the device they live on: what GetFlow / GetPotential serve from the host copies.  For the
+ * multi-GPU result gather of a batch, which sends the records GPU -> GPU over NCCL without a host bounce.
+ * Valid until the next call that solves, probes or destroys the handle.  MCF_ERR_NOT_OPTIMAL unless Optimal. */
+int mcf_get_device_results(mcf_handle* h, const int64_t** flow_dev_out, const int64_t** potential_dev_out, int32_t* device_out);
+
 /* Batches of independent instances (BASELINE.json config 5): instance i is solved on devices[i % n_devices],
  * one host thread per device.  statuses_out[count] receives each instance's mcf_status. */
 int mcf_solve_batch(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t* statuses_out);

@@ -347,7 +347,7 @@ int upload_team(mcf_handle* h, int team, int slice, int wide, mcf::TeamParams* P
     int rep_ent = 1, rep_cyc = 1;
     mcfk_team_replicas(&rep_ent, &rep_cyc);
     const size_t w_ent = (size_t)2 * rep_ent * mcf::kMailWords;
-    const size_t w_cyc = (size_t)2 * rep_cyc * team * mcf::kMailWords;
+    const size_t w_cyc = (size_t)2 * rep_cyc * 5 * ((team + 7) & ~7);           // word-major: [2][replica][word 0..4][team padded to 8]
     const size_t w_stage = (size_t)2 * mcf::kReqMax;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
     const size_t seg_off = (w_ent + w_cyc + w_stage + 7) & ~(size_t)7;
@@ -807,6 +807,16 @@ int mcf_get_metrics(mcf_handle* h, mcf_metrics* out)
     if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
     if (!h->solved_once) return fail(h, MCF_ERR_NOT_SOLVED, "Solve() has not been called");
     *out = h->metrics; return MCF_OK;
+}
+
+int mcf_get_device_results(mcf_handle* h, const int64_t** flow_dev_out, const int64_t** potential_dev_out, int32_t* device_out)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    if (h->status != MCF_OPTIMAL || !h->d_pi_final || !h->d_flow.p) return fail(h, MCF_ERR_NOT_OPTIMAL, "Solution not optimal");
+    if (flow_dev_out) *flow_dev_out = reinterpret_cast<const int64_t*>(h->d_flow.p);
+    if (potential_dev_out) *potential_dev_out = reinterpret_cast<const int64_t*>(h->d_pi_final);
+    if (device_out) *device_out = h->device_bound;
+    return MCF_OK;
 }
 
 int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* devices, int32_t n_devices, int32_t per_device, int32_t* statuses_out)

@@ -119,7 +119,7 @@ struct TeamParams {
     long long* pi;                                       // [n+1] potentials (NS.cs:48); every entry is read and written by its owner CTA only
     const int* in0; const int* sz0; const int* pd0; const int* dp0;   // [n+1] initial basis: depth-first index, subtree size, pred word, depth
     int4* ent;                                           // [2][kRepEnt][kMailWords]        pricer -> all: entering arc of the pivot + staging requests
-    int4* cyc;                                           // [2][kRepCyc][team][kMailWords]  owner -> all: leaving-arc candidates
+    int4* cyc;                                           // [2][kRepCyc][5][team padded to 8] owner -> all: leaving-arc candidates, word-major
     int4* stemseg;                                       // [2][n+1][2]                     stem entries, indexed by depth
     int4* stage;                                         // [2 * kReqMax]                   owner -> pricer: {pi, in} of the arc ends of a requested range
     Ctl* ctl;

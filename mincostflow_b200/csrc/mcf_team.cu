@@ -43,7 +43,6 @@ constexpr int kRepEnt = 4;                              // replicas of the ENTER
 constexpr int kRepCyc = 4;                              // replicas of every CYC record
 constexpr int kRelUnroll = 4;                           // nodes per thread in flight in the relabel pass
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
-constexpr int kSrvU = 8;                                // arcs per owner thread in flight while serving a staging request
 
 // mailbox words: one 128-bit relaxed.gpu access each (single-copy atomic, PTX ISA 8.3+), polled until the sequence number matches
 __device__ __forceinline__ int4 ld_mail(const int4* p)
@@ -102,11 +101,11 @@ struct Cand {                       // leaving-arc candidate of one side of the 
 };
 
 struct PWin {                       // a pricing candidate
-    long long rc;
+    long long rc;                   // reduced cost state * (cost + pi_s - pi_t), negative when valid
     int off;                        // scan offset from next_arc (< 0: none)
-    int arc, src, tgt, cost, state, in_s, in_t;
+    int arc, src, tgt, state, in_s, in_t;
     int blk;                        // block of the scan the candidate lies in (later rounds of a search)
-    long long pi_s, pi_t, upper;
+    long long rcb, upper;           // cost + pi_s - pi_t; capacity
 };
 
 struct Book {                       // statistics and timers: touched by thread 0 only, kept out of the register file
@@ -124,8 +123,8 @@ struct Pending {                    // one pivot's update in closed form: what t
 };
 
 struct Ent {                        // the entering arc of a pivot as every CTA knows it
-    int arc, src, tgt, cost, state, in_s, in_t;
-    long long upper, pi_s, pi_t;
+    int arc, src, tgt, state, in_s, in_t;
+    long long upper, rcb;           // capacity; cost + pi_s - pi_t (all that UpdatePotentials needs of the potentials, NS.cs:1187-1188)
 };
 
 struct Dec {                        // the decision of a pivot (FindLeavingArc, NS.cs:943-1010), identical in every CTA
@@ -148,7 +147,7 @@ struct TeamShared {
     Cand wc[2][kTW];                // per-warp winners (CYC gather, owner slow path)
     PWin pw[kTW];                   // per-warp pricing winners
     PWin win;                       // entering arc of this pivot (pricer)
-    int4 ent[6];                    // ENTER record as received (owners)
+    int4 ent[5];                    // ENTER record as received (owners): words 0-3 the entering arc, word 4 the staging request
     int ncand, abort, cnt, mode, dpF, dpS, ovf;
 };
 
@@ -194,7 +193,7 @@ __device__ __forceinline__ bool poll_rec(const int4* rec, int seq, int4 (&w)[NW]
 
 __device__ __forceinline__ PWin pwin_none()
 {
-    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.cost = w.state = w.in_s = w.in_t = w.blk = 0; w.pi_s = w.pi_t = w.upper = 0;
+    PWin w; w.rc = 0; w.off = -1; w.arc = -1; w.src = w.tgt = w.state = w.in_s = w.in_t = w.blk = 0; w.rcb = w.upper = 0;
     return w;
 }
 __device__ __forceinline__ Cand cand_none() { Cand c; c.d = 0; c.in = c.sz = c.zero = c.dp = c.j = 0; c.pd = -1; return c; }
@@ -224,6 +223,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = P.team, cta = blockIdx.x, nown = G - 1;
+    const int Gp = (G + 7) & ~7;                         // CYC word arrays are padded to whole 128-byte lines
     const int n = P.n, S = P.S;
     const bool pricer = cta == 0;
     const int own = cta - 1;
@@ -246,14 +246,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
     // pricer: arc data and both ends' node records of the staged block [pf_next, pf_next + pf_B)
     long long* const pf_up = reinterpret_cast<long long*>(body);
-    long long* const pf_pis = pf_up + kStageMax;
-    long long* const pf_pit = pf_pis + kStageMax;
-    int* const pf_src = reinterpret_cast<int*>(pf_pit + kStageMax);
+    long long* const pf_rcb = pf_up + kStageMax;                                // cost + pi_s - pi_t as of the basis the records were served from
+    int2* const pf_lab = reinterpret_cast<int2*>(pf_rcb + kStageMax);           // {in[src], in[tgt]} as of the same basis
+    int* const pf_src = reinterpret_cast<int*>(pf_lab + kStageMax);
     int* const pf_tgt = pf_src + kStageMax;
     int* const pf_cost = pf_tgt + kStageMax;
     int* const pf_st = pf_cost + kStageMax;
-    int* const pf_ins = pf_st + kStageMax;
-    int* const pf_int = pf_ins + kStageMax;
 
     int status = ST_NOT_SOLVED;
     {
@@ -317,7 +315,6 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         const bool lower_state = E.state == STATE_LOWER;
         const int first = lower_state ? E.src : E.tgt, second = lower_state ? E.tgt : E.src;      // NS.cs:948-957
         const int inF = lower_state ? E.in_s : E.in_t, inS = lower_state ? E.in_t : E.in_s;
-        const long long piF = lower_state ? E.pi_s : E.pi_t, piS = lower_state ? E.pi_t : E.pi_s;
         if (tid == 0) { sh.cnt = 0; sh.ncand = 0; }
         __syncthreads();
         const int nw = (nown + 31) >> 5;                                            // warps that poll
@@ -325,15 +322,28 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             Cand b1 = cand_none(), b2 = cand_none();
             int c = 0;
             if (tid < nown) {
-                int4 w[5];
-                if (!poll_rec<5>(P.cyc + (((size_t)par * kRepCyc + cta % kRepCyc) * G + 1 + tid) * kMailWords, seq, w, P)) sh.abort = 1;
+                // the records are stored word-major (word w of every owner side by side): consecutive lanes poll consecutive
+                // 16-byte words of the same lines.  Word 0 says whether the owner has candidates at all; only then are words 1-4 read.
+                const int4* const wbase = P.cyc + ((size_t)par * kRepCyc + cta % kRepCyc) * 5 * Gp + 1 + tid;
+                int4 w0;
+                if (!poll_word(wbase, seq, w0, P)) sh.abort = 1;
                 else {
-                    const int f = w[0].x;
+                    const int f = w0.x;
                     c = f & 0xffff;
-                    if (f & (1 << 18)) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.dp = w[2].z; b1.zero = (f >> 16) & 1; }
-                    if (f & (1 << 19)) { b2.d = mk64(w[3].x, w[3].y); b2.in = w[3].z; b2.sz = w[4].x; b2.pd = w[4].y; b2.dp = w[4].z; b2.zero = (f >> 17) & 1; }
-                    if (f & (1 << 20)) sh.dpF = w[0].y;
-                    if (f & (1 << 21)) sh.dpS = w[0].z;
+                    if (f & (3 << 18)) {
+                        int4 w[4];
+                        unsigned spins = 0; long long t0 = 0;
+                        for (;;) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) w[i] = ld_mail(wbase + (size_t)(i + 1) * Gp);
+                            if (w[0].w == seq && w[1].w == seq && w[2].w == seq && w[3].w == seq) break;
+                            if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                        }
+                        if (f & (1 << 18)) { b1.d = mk64(w[0].x, w[0].y); b1.in = w[0].z; b1.sz = w[1].x; b1.pd = w[1].y; b1.dp = w[1].z; b1.zero = (f >> 16) & 1; }
+                        if (f & (1 << 19)) { b2.d = mk64(w[2].x, w[2].y); b2.in = w[2].z; b2.sz = w[3].x; b2.pd = w[3].y; b2.dp = w[3].z; b2.zero = (f >> 17) & 1; }
+                    }
+                    if (f & (1 << 20)) sh.dpF = w0.y;
+                    if (f & (1 << 21)) sh.dpS = w0.z;
                     if (f & (1 << 22)) sh.ovf = 2;
                 }
             }
@@ -349,10 +359,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (sh.abort) [[unlikely]] return ST_ERR_BARRIER_TIMEOUT;
         if (sh.ovf == 2) [[unlikely]] return ST_ERR_NEEDS_WIDE;                     // every CTA reads every record: all leave on the same pivot
         Cand w1 = cand_none(), w2 = cand_none();
-        for (int w = 0; w < nw; ++w) {
-            const Cand t1 = sh.wc[0][w], t2 = sh.wc[1][w];
-            if (t1.pd >= 0 && (w1.pd < 0 || t1.d < w1.d || (t1.d == w1.d && t1.in > w1.in))) w1 = t1;
-            if (t2.pd >= 0 && (w2.pd < 0 || t2.d < w2.d || (t2.d == w2.d && t2.in < w2.in))) w2 = t2;
+        {   // second stage, redundantly in every warp: lane w looks at the winners of polling warp w
+            const int wl = lane < nw ? lane : 0;
+            const long long d1 = sh.wc[0][wl].d, d2 = sh.wc[1][wl].d;
+            const int i1 = sh.wc[0][wl].in, i2 = sh.wc[1][wl].in;
+            const int l1 = warp_argmin(lane < nw && sh.wc[0][wl].pd >= 0, d1, -i1), l2 = warp_argmin(lane < nw && sh.wc[1][wl].pd >= 0, d2, i2);
+            if (l1 >= 0) w1 = sh.wc[0][l1];
+            if (l2 >= 0) w2 = sh.wc[1][l2];
         }
         const bool has1 = w1.pd >= 0, has2 = w2.pd >= 0;
         const int cnt = sh.cnt;
@@ -421,10 +434,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             TICK(t_stem);
         }
         if (change && tid == 0) { if (ns > sh.bk.max_stem) sh.bk.max_stem = ns; sh.bk.moved_nodes += s; }
-        const long long piU = in_side1 ? piF : piS, piV = in_side1 ? piS : piF;
         U.valid = 1; U.change = change ? 1 : 0; U.a = a; U.s = s; U.b = b; U.ns = ns; U.longstem = longstem ? 1 : 0;
         U.dshift = dp_vin + 1 - dp_uin; U.par = par; U.seq = seq;
-        U.sigma = piV - piU - (D.dir_new_up ? (long long)E.cost : -(long long)E.cost);                // NS.cs:1187-1188
+        U.sigma = D.dir_new_up ? -E.rcb : E.rcb;     // pi[v_in] - pi[u_in] -/+ cost (NS.cs:1187-1188), u_in being the source or the target
         return 0;
     };
 
@@ -436,11 +448,6 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         long long pf_upto = 0;                           // ... with node records as of "all updates of pivots <= pf_upto applied"
         int ticket = 0;                                  // last staging request issued
         unsigned pf_missing = 0;                         // bit j: record pair of arc (tid + j * kTT) of the staged block not yet collected
-        // arc-state changes of the last two pivots: applied on top of whatever a scan reads (staged or global), newest first
-        int patch_arc0 = -1, patch_st0 = 0, patch_arc1 = -1, patch_st1 = 0, patch2_arc0 = -1, patch2_st0 = 0, patch2_arc1 = -1, patch2_st1 = 0;
-        auto fix_state = [&](int idx, int st) -> int {
-            return idx == patch_arc0 ? patch_st0 : idx == patch_arc1 ? patch_st1 : idx == patch2_arc0 ? patch2_st0 : idx == patch2_arc1 ? patch2_st1 : st;
-        };
         Pending Uprev;                                   // the previous pivot's update, replayed on the staged node records
         Uprev.valid = Uprev.change = Uprev.a = Uprev.s = Uprev.b = Uprev.longstem = Uprev.dshift = Uprev.par = Uprev.seq = 0; Uprev.ns = 1; Uprev.sigma = 0;
 
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         };
         // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage[]" (word 5 of the ENTER line)
         auto post_request = [&](int par, int seq, int cursor, int cnt, int tk) {
-            if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 5, make_int4(cursor, cnt, tk, seq));
+            if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 4, make_int4(cursor, cnt, tk, seq));
         };
         auto arm_collect = [&](int cnt) {
             pf_missing = 0;
@@ -483,7 +490,11 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) if (pf_missing >> (jb + j) & 1u) {
                         const int q = tid + (jb + j) * kTT;
-                        if (vs[j].w == tk && vt[j].w == tk) { pf_pis[q] = mk64(vs[j].x, vs[j].y); pf_ins[q] = vs[j].z; pf_pit[q] = mk64(vt[j].x, vt[j].y); pf_int[q] = vt[j].z; pf_missing &= ~(1u << (jb + j)); }
+                        if (vs[j].w == tk && vt[j].w == tk) {
+                            pf_rcb[q] = (long long)pf_cost[q] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            pf_lab[q] = make_int2(vs[j].z, vt[j].z);
+                            pf_missing &= ~(1u << (jb + j));
+                        }
                     }
                 }
                 if (!block) return pf_missing == 0;
@@ -517,32 +528,31 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // applied (pf_upto == k - 2); that one update is replayed here from its closed form, so pricing waits for nobody.
             {
                 const bool replay = pf_upto < k - 1 && Uprev.change;
-                long long b_rc = 0, b_ps = 0, b_pt = 0;
-                int bq = -1, b_st = 0;
-#pragma unroll
-                for (int j = 0; j < kPf; ++j) {
-                    const int q = tid + j * kTT;
-                    if (q < blk0) {
-                        int idx = next_arc + q; if (idx >= S) idx -= S;
-                        const int st = fix_state(idx, pf_st[q]);
-                        long long ps = pf_pis[q], pt = pf_pit[q];
-                        if (replay) {                                    // UpdatePotentials of the pending pivot (NS.cs:1185-1209)
-                            if ((unsigned)(pf_ins[q] - Uprev.a) < (unsigned)Uprev.s) ps += Uprev.sigma;
-                            if ((unsigned)(pf_int[q] - Uprev.a) < (unsigned)Uprev.s) pt += Uprev.sigma;
-                        }
-                        const long long rc = (long long)st * ((long long)pf_cost[q] + ps - pt);
-                        if (rc < b_rc) { b_rc = rc; bq = q; b_st = st; b_ps = ps; b_pt = pt; }
-                    }
+                const unsigned ra = replay ? (unsigned)Uprev.a : 0u, rs = replay ? (unsigned)Uprev.s : 0u;   // rs == 0: nothing matches
+                const long long sg = Uprev.sigma;
+                long long b_rc = 0;
+                int bq = -1;
+                for (int q = tid; q < blk0; q += kTT) {
+                    const int st = pf_st[q];
+                    const int2 lab = pf_lab[q];
+                    long long v = pf_rcb[q];
+                    // UpdatePotentials of the pending pivot (NS.cs:1185-1209): pi += sigma inside the re-hung interval
+                    if ((unsigned)lab.x - ra < rs) v += sg;
+                    if ((unsigned)lab.y - ra < rs) v -= sg;
+                    const long long rc = st > 0 ? v : (st < 0 ? -v : 0);
+                    if (rc < b_rc) { b_rc = rc; bq = q; }
                 }
                 const int wl = warp_argmin(bq >= 0, b_rc, bq);
                 if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
                 else if (lane == wl) {
                     PWin best;
-                    best.rc = b_rc; best.off = bq; best.state = b_st; best.pi_s = b_ps; best.pi_t = b_pt; best.blk = 0;
+                    best.rc = b_rc; best.off = bq; best.state = pf_st[bq]; best.blk = 0;
                     int idx = next_arc + bq; if (idx >= S) idx -= S;
                     best.arc = idx;
-                    best.src = pf_src[bq]; best.tgt = pf_tgt[bq]; best.cost = pf_cost[bq]; best.upper = pf_up[bq];
-                    best.in_s = pf_ins[bq]; best.in_t = pf_int[bq];
+                    best.src = pf_src[bq]; best.tgt = pf_tgt[bq]; best.upper = pf_up[bq];
+                    const int2 lab = pf_lab[bq];
+                    best.in_s = lab.x; best.in_t = lab.y;
+                    best.rcb = best.state > 0 ? b_rc : -b_rc;
                     if (replay) {                                        // the winner's labels as they are after the pending update
                         int nx, nd;
                         relabel(Uprev, best.in_s, 0, nx, nd); best.in_s = nx;
@@ -556,18 +566,19 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int ww = warp_argmin(lane < kTW && qv->off >= 0, qv->rc, qv->off);
                 if (ww >= 0) { have_win = true; search_end = blk0; if (tid == 0) sh.win = sh.pw[ww]; }
             }
+            PROBE(0);
             if (!have_win && blk0 < S) [[unlikely]] {
                 // ---- later rounds: M consecutive blocks per round straight from global memory; their node records are requested
                 // from the owners (who hold the basis as of update k-1: no replay).  The lowest block with a negative reduced cost
                 // wins, inside it the smallest reduced cost, then the first in scan order.
-                const long long nblk = ((long long)S + B - 1) / B;
-                long long next_blk = 1;
+                const int nblk = (S + B - 1) / B;
+                int next_blk = 1;
                 int found_blk = -1;
                 for (int r = 1; found_blk < 0 && next_blk < nblk; ++r) {
                     const int mcap = max(1, kReqMax / B);
-                    const int M = min(mcap, r < 4 ? 1 << (r - 1) : 8);
-                    const long long b_lo = next_blk, b_hi = min(nblk, b_lo + M);
-                    const long long o_lo = b_lo * B; long long o_hi = b_hi * B; if (o_hi > S) o_hi = S;
+                    const int M = min(mcap, r < 2 ? 2 : 8);
+                    const int b_lo = next_blk, b_hi = min(nblk, b_lo + M);
+                    const long long o_lo = (long long)b_lo * B; long long o_hi = (long long)b_hi * B; if (o_hi > S) o_hi = S;
                     const int cnt = (int)(o_hi - o_lo);
                     int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
                     ++ticket;
@@ -576,22 +587,22 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     PWin best = pwin_none();
                     unsigned spins = 0; long long t0 = 0;
                     for (int off = tid; off < cnt; off += kTT) {
-                        const int blk = (int)b_lo + off / B;
+                        const int blk = b_lo + off / B;
                         if (best.off >= 0 && blk > best.blk) break;     // a thread's offsets ascend: later blocks cannot win
                         int idx = cur + off; if (idx >= S) idx -= S;
                         const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
-                        const int st = fix_state(idx, __ldcg(P.state + idx));
+                        const int st = __ldcg(P.state + idx);
                         int4 vs, vt;
                         for (;;) {
                             vs = ld_mail(P.stage + 2 * off); vt = ld_mail(P.stage + 2 * off + 1);
                             if (vs.w == ticket && vt.w == ticket) break;
                             if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
                         }
-                        const long long ps = mk64(vs.x, vs.y), pt = mk64(vt.x, vt.y);
-                        const long long rc = (long long)st * ((long long)c + ps - pt);
+                        const long long v = (long long)c + mk64(vs.x, vs.y) - mk64(vt.x, vt.y);
+                        const long long rc = st > 0 ? v : (st < 0 ? -v : 0);
                         if (rc < best.rc) {
-                            best.rc = rc; best.off = (int)o_lo + off; best.blk = blk; best.arc = idx; best.src = s; best.tgt = t; best.cost = c; best.state = st;
-                            best.in_s = vs.z; best.in_t = vt.z; best.pi_s = ps; best.pi_t = pt;
+                            best.rc = rc; best.off = (int)o_lo + off; best.blk = blk; best.arc = idx; best.src = s; best.tgt = t; best.state = st;
+                            best.in_s = vs.z; best.in_t = vt.z; best.rcb = v;
                         }
                     }
                     {   // lowest block first, then (rc, off)
@@ -618,6 +629,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     search_end = (int)e; have_win = true;
                 } else search_end = S;
             } else if (!have_win) search_end = S;
+            PROBE(6);
             // NS.cs:1397-1438: cursor, counters, adaptive block size
             if (tid == 0) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
             int cons_low_new = 0, cons_high_new = 0;
@@ -636,25 +648,24 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     cons_low_new = cl; cons_high_new = ch;
                 }
                 // `_nextArc = e` (NS.cs:1397): the last arc examined, or unchanged after a full sweep that ended inside a block
-                if (search_end < S || (long long)S % Bold == 0) { int e = next_arc + search_end - 1; if (e >= S) e -= S; next_arc = e; }
+                if (search_end < S || S % Bold == 0) { int e = next_arc + search_end - 1; if (e >= S) e -= S; next_arc = e; }
             }
             __syncthreads();                                            // sh.win is written; cons_low / cons_high were read
             if (tid == 0 && P.adaptive && have_win) { sh.bk.cons_low = cons_low_new; sh.bk.cons_high = cons_high_new; }
             // ---- post ENTER(k) (+ the request for the next pivot's block: exactly known now)
             const int nb0 = B < S ? B : S;
             if (have_win) ++ticket;
-            if (warp == 0 && lane < 6 * kRepEnt) {
+            if (warp == 0 && lane < 5 * kRepEnt) {
                 const PWin& w = sh.win;
-                const int wd = lane % 6;
+                const int wd = lane % 5;
                 int4 o;
                 if (!have_win) o = make_int4(-1, 0, 0, seq);
                 else if (wd == 0) o = make_int4(w.arc, w.src, w.tgt, seq);
-                else if (wd == 1) o = make_int4(w.cost, w.state, 0, seq);
-                else if (wd == 2) o = make_int4(w.in_s, w.in_t, 0, seq);
-                else if (wd == 3) o = make_int4(lo32(w.pi_s), hi32(w.pi_s), lo32(w.upper), seq);
-                else if (wd == 4) o = make_int4(lo32(w.pi_t), hi32(w.pi_t), hi32(w.upper), seq);
+                else if (wd == 1) o = make_int4(w.state, w.in_s, w.in_t, seq);
+                else if (wd == 2) o = make_int4(lo32(w.rcb), hi32(w.rcb), 0, seq);
+                else if (wd == 3) o = make_int4(lo32(w.upper), hi32(w.upper), 0, seq);
                 else o = make_int4(next_arc, nb0, ticket, seq);
-                if (have_win || wd < 5) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 6) * kMailWords + wd, o);
+                if (have_win || wd < 4) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 5) * kMailWords + wd, o);
             }
             TICK(t_price);
             PROBE(1);
@@ -676,8 +687,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             Ent E;
             {
                 const PWin& w = sh.win;
-                E.arc = w.arc; E.src = w.src; E.tgt = w.tgt; E.cost = w.cost; E.state = w.state; E.in_s = w.in_s; E.in_t = w.in_t;
-                E.upper = w.upper; E.pi_s = w.pi_s; E.pi_t = w.pi_t;
+                E.arc = w.arc; E.src = w.src; E.tgt = w.tgt; E.state = w.state; E.in_s = w.in_s; E.in_t = w.in_t;
+                E.upper = w.upper; E.rcb = w.rcb;
             }
             // off the critical path: finish the arc data of the next block, a first look at the served node records
             stage_static_finish(next_arc, nb0);
@@ -686,20 +697,27 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<true>(seq, par, E, 0, D, U);
             if (rcd != 0) { status = rcd; break; }
-            // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them
-            patch2_arc0 = patch_arc0; patch2_st0 = patch_st0; patch2_arc1 = patch_arc1; patch2_st1 = patch_st1;
-            if (D.change) { patch_arc0 = E.arc; patch_st0 = STATE_TREE; patch_arc1 = D.out.pd >> 1; patch_st1 = (D.out.zero & 1) ? STATE_LOWER : STATE_UPPER; }
-            else { patch_arc0 = E.arc; patch_st0 = -E.state; patch_arc1 = -1; }
+            // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them - state[] in global memory and, when the arc
+            // lies in the block staged for the next pivot, its copy in shared memory (staged before this decision)
             if (tid == 0) {
-                P.state[patch_arc0] = patch_st0;
-                if (patch_arc1 >= 0) P.state[patch_arc1] = patch_st1;
+                const int arc0 = E.arc, st0 = D.change ? STATE_TREE : -E.state;
+                const int arc1 = D.change ? D.out.pd >> 1 : -1, st1 = (D.out.zero & 1) ? STATE_LOWER : STATE_UPPER;
+                P.state[arc0] = st0;
+                int q0 = arc0 - next_arc; if (q0 < 0) q0 += S;
+                if (q0 < nb0) pf_st[q0] = st0;
+                if (arc1 >= 0) {
+                    P.state[arc1] = st1;
+                    int q1 = arc1 - next_arc; if (q1 < 0) q1 += S;
+                    if (q1 < nb0) pf_st[q1] = st1;
+                }
             }
             Uprev = U;                                                              // replayed by the next pricing (see above)
+            PROBE(5);
             // the served node records of the next block: whatever had not arrived before the CYC gather
             if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
             pf_next = next_arc; pf_B = nb0; pf_upto = k - 1;
             TICK(t_update);
-            PROBE(5);
+            PROBE(7);
             if (P.stop_after > 0 && iterations >= P.stop_after) { status = ST_STOPPED_EARLY; break; }
         }
         if (tid == 0) sh.mode = B;                                                   // final block size, for the epilogue
@@ -709,21 +727,36 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // serve a staging request: for every end of arcs [cursor, cursor + cnt) that this CTA owns, write {pi, in, ticket} - the
         // node's record as of the basis this CTA holds right now - into the pricer's staging slots
         auto serve = [&](int cursor, int cnt, int tk) {
-            for (int base = 0; base < cnt; base += kSrvU * kTT) {
-                int sid[kSrvU], did[kSrvU];
+            // the range is one or (when it wraps at S) two linear pieces of the arc arrays; each is read as aligned 128-bit words
+            int seg_a = cursor, seg_n = min(cnt, S - cursor), off0 = 0;
+            for (int piece = 0; piece < 2 && seg_n > 0; ++piece) {
+                const int a0 = seg_a & ~3;
+                const int nch = ((seg_a + seg_n + 3) >> 2) - (a0 >> 2);
+                for (int ch0 = tid; ch0 < nch; ch0 += 2 * kTT) {            // two chunks of four arcs per thread in flight
+                    int4 s4[2], t4[2];
 #pragma unroll
-                for (int e = 0; e < kSrvU; ++e) {
-                    const int off = base + e * kTT + tid;
-                    sid[e] = did[e] = -1;
-                    if (off < cnt) { int idx = cursor + off; if (idx >= S) idx -= S; sid[e] = __ldg(P.src + idx); did[e] = __ldg(P.tgt + idx); }
-                }
+                    for (int u = 0; u < 2; ++u) {
+                        const int ch = ch0 + u * kTT;
+                        if (ch < nch) { s4[u] = __ldg(reinterpret_cast<const int4*>(P.src + a0) + ch); t4[u] = __ldg(reinterpret_cast<const int4*>(P.tgt + a0) + ch); }
+                    }
 #pragma unroll
-                for (int e = 0; e < kSrvU; ++e) {
-                    const int off = base + e * kTT + tid;
-                    const unsigned js = (unsigned)(sid[e] - lo), jt = (unsigned)(did[e] - lo);
-                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sid[e]); st_mail(P.stage + 2 * off, make_int4(lo32(p), hi32(p), in_s[js], tk)); }
-                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + did[e]); st_mail(P.stage + 2 * off + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
+                    for (int u = 0; u < 2; ++u) {
+                        const int ch = ch0 + u * kTT;
+                        if (ch < nch) {
+                            const int sv[4] = {s4[u].x, s4[u].y, s4[u].z, s4[u].w}, tv[4] = {t4[u].x, t4[u].y, t4[u].z, t4[u].w};
+                            const int ob = a0 + 4 * ch - seg_a;                 // offset of the chunk's first arc inside the piece
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if ((unsigned)(ob + e) < (unsigned)seg_n) {
+                                    const unsigned js = (unsigned)(sv[e] - lo), jt = (unsigned)(tv[e] - lo);
+                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(P.stage + 2 * (off0 + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
+                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(P.stage + 2 * (off0 + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
+                                }
+                            }
+                        }
+                    }
                 }
+                off0 += seg_n; seg_a = 0; seg_n = cnt - off0;
             }
         };
         for (;;) {
@@ -738,20 +771,20 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     int4 v = make_int4(0, 0, 0, 0);
                     int mode = 0;
                     for (;;) {
-                        if (lane < 6) v = ld_mail(line + lane);
-                        const unsigned okm = __ballot_sync(0xffffffffu, lane < 6 && v.w == seq);
-                        if ((okm & 0x1fu) == 0x1fu) { mode = 1; break; }
-                        const int tk = __shfl_sync(0xffffffffu, v.z, 5);
-                        if ((okm & 0x20u) && tk != ticket) { mode = 2; break; }
+                        if (lane < 5) v = ld_mail(line + lane);
+                        const unsigned okm = __ballot_sync(0xffffffffu, lane < 5 && v.w == seq);
+                        if ((okm & 0xfu) == 0xfu) { mode = 1; break; }
+                        const int tk = __shfl_sync(0xffffffffu, v.z, 4);
+                        if ((okm & 0x10u) && tk != ticket) { mode = 2; break; }
                         if (spin_check(spins, t0, P)) { mode = 3; break; }
                     }
-                    if (lane < 6) sh.ent[lane] = v;
+                    if (lane < 5) sh.ent[lane] = v;
                     if (lane == 0) sh.mode = mode;
                 }
                 __syncthreads();
                 const int mode = sh.mode;
                 if (mode == 2) {
-                    const int4 rq = sh.ent[5];
+                    const int4 rq = sh.ent[4];
                     serve(rq.x, rq.y, rq.z); ticket = rq.z;
                     __syncthreads();
                     continue;
@@ -763,10 +796,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             Ent E;
             int4 nreq;                                                   // the staging request that came with ENTER(k)
             {
-                const int4 r0 = sh.ent[0], r1 = sh.ent[1], r2 = sh.ent[2], r3 = sh.ent[3], r4 = sh.ent[4];
-                nreq = sh.ent[5];
-                E.arc = r0.x; E.src = r0.y; E.tgt = r0.z; E.cost = r1.x; E.state = r1.y; E.in_s = r2.x; E.in_t = r2.y;
-                E.pi_s = mk64(r3.x, r3.y); E.pi_t = mk64(r4.x, r4.y); E.upper = mk64(r3.z, r4.z);
+                const int4 r0 = sh.ent[0], r1 = sh.ent[1], r2 = sh.ent[2], r3 = sh.ent[3];
+                nreq = sh.ent[4];
+                E.arc = r0.x; E.src = r0.y; E.tgt = r0.z; E.state = r1.x; E.in_s = r1.y; E.in_t = r1.z;
+                E.rcb = mk64(r2.x, r2.y); E.upper = mk64(r3.x, r3.y);
             }
             if (E.arc < 0) { status = ST_OPTIMAL; break; }
             iterations = k;
@@ -807,15 +840,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const int nc = sh.ncand;
             PROBE(10);
             {
-                // the record goes out in kRepCyc copies (lane l writes word l % 5 of copy l / 5)
-                int4* const rec = P.cyc + (((size_t)par * kRepCyc + lane / 5) * G + cta) * kMailWords;
+                // the record goes out in kRepCyc copies (lane l writes word l % 5 of copy l / 5), stored word-major
+                int4* const rec = P.cyc + ((size_t)par * kRepCyc + lane / 5) * 5 * Gp + cta;
                 // word 0 also carries the depth of the entering arc's ends (whoever owns them) and the int32-overflow flag of narrow mode
                 int w0x = nc > 0xffff ? 0xffff : nc, dF = 0, dS = 0;
                 if ((unsigned)(first - lo) < (unsigned)cntn) { w0x |= 1 << 20; dF = dp_s[first - lo]; }
                 if ((unsigned)(second - lo) < (unsigned)cntn) { w0x |= 1 << 21; dS = dp_s[second - lo]; }
                 if (sh.ovf) w0x |= 1 << 22;
                 if (nc == 0) {
-                    if (warp == 0 && lane < 5 * kRepCyc) st_mail(rec + lane % 5, make_int4(lane % 5 == 0 ? w0x : 0, dF, dS, seq));
+                    if (warp == 0 && lane < 5 * kRepCyc && lane % 5 == 0) st_mail(rec, make_int4(w0x, dF, dS, seq));       // no candidates: word 0 is all anyone reads
                 } else {
                     Cand m1 = cand_none(), m2 = cand_none();
                     if (nc <= kCandCap) {
@@ -864,7 +897,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         else if (wd == 2) w = make_int4(m1.sz, m1.pd, m1.dp, seq);
                         else if (wd == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
                         else w = make_int4(m2.sz, m2.pd, m2.dp, seq);
-                        st_mail(rec + wd, w);
+                        st_mail(rec + (size_t)wd * Gp, w);
                     }
                 }
             }
@@ -876,14 +909,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     int4 v = make_int4(0, 0, 0, 0);
                     unsigned spins = 0; long long t0 = 0;
                     for (;;) {
-                        v = ld_mail(line + 5);
+                        v = ld_mail(line + 4);
                         if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
                         if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
                     }
-                    sh.ent[5] = v;
+                    sh.ent[4] = v;
                 }
                 __syncthreads();
-                nreq = sh.ent[5];
+                nreq = sh.ent[4];
             }
             if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
             PROBE(8);
@@ -949,23 +982,32 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (change) {
                 const int b = U.b;
                 const int sh_lo = b < a ? b + 1 : a + s, sh_len = b < a ? a - b - 1 : b - a - s + 1, sh_by = b < a ? s : -s;
-                // four independent nodes per thread in flight
-                for (int j0 = tid; j0 < cntn; j0 += kRelUnroll * kTT) {
-                    int xv[kRelUnroll];
+                // four nodes per 128-bit shared-memory access; padding entries carry label 0, which no update ever moves
+                const int nquad = cntn > 0 ? (cntn + 3) >> 2 : 0;
+                for (int q4 = tid; q4 < nquad; q4 += kTT) {
+                    int4 v = reinterpret_cast<const int4*>(in_s)[q4];
+                    int xi[4] = {v.x, v.y, v.z, v.w};
+                    bool touched = false, moved = false;
 #pragma unroll
-                    for (int e = 0; e < kRelUnroll; ++e) { const int j = j0 + e * kTT; xv[e] = j < cntn ? in_s[j] : 0; }
-#pragma unroll
-                    for (int e = 0; e < kRelUnroll; ++e) {
-                        const int x = xv[e], j = j0 + e * kTT;
-                        if ((unsigned)(x - sh_lo) < (unsigned)sh_len) {                // between the old and the new place: shift
-                            in_s[j] = x + sh_by;
-                        } else if ((unsigned)(x - a) < (unsigned)s) {                  // re-hung subtree
-                            int nx, nd;
-                            relabel(U, x, dp_s[j], nx, nd);
-                            in_s[j] = nx; dp_s[j] = nd;
-                            if (U.sigma != 0) __stcg(P.pi + lo + j, __ldcg(P.pi + lo + j) + U.sigma);   // this CTA is the entry's only reader and writer
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        if ((unsigned)(xi[e] - sh_lo) < (unsigned)sh_len) { xi[e] += sh_by; touched = true; }      // between the old and the new place: shift
+                        else if ((unsigned)(xi[e] - a) < (unsigned)s) moved = true;                             // re-hung subtree
                     }
+                    if (moved) {
+#pragma unroll 1
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = q4 * 4 + e;
+                            const int x = e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w;
+                            if ((unsigned)(x - a) < (unsigned)s && !((unsigned)(x - sh_lo) < (unsigned)sh_len)) {
+                                int nx, nd;
+                                relabel(U, x, dp_s[j], nx, nd);
+                                xi[e] = nx; dp_s[j] = nd;
+                                if (U.sigma != 0) __stcg(P.pi + lo + j, __ldcg(P.pi + lo + j) + U.sigma);   // this CTA is the entry's only reader and writer
+                            }
+                        }
+                        touched = true;
+                    }
+                    if (touched) reinterpret_cast<int4*>(in_s)[q4] = make_int4(xi[0], xi[1], xi[2], xi[3]);
                 }
             }
             if (bad) sh.ovf = 1;                                                    // goes out with CYC(k+1)
@@ -1030,7 +1072,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
-constexpr size_t kPricerBytes = (size_t)mcf::kStageMax * (3 * 8 + 6 * 4);
+constexpr size_t kPricerBytes = (size_t)mcf::kStageMax * (3 * 8 + 4 * 4);   // up, rcb, lab + src, tgt, cost, st
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 

@@ -431,6 +431,12 @@ class NetworkSimplex:
             self._pots = out
         return self._pots
 
+    def device_results(self):
+        """(flow pointer, potential pointer, device) of the result arrays in HBM (mcf_get_device_results)."""
+        f = C.c_void_p(); p = C.c_void_p(); d = C.c_int32(-1)
+        self._check(self._lib.mcf_get_device_results(self._h, C.byref(f), C.byref(p), C.byref(d)))
+        return f.value, p.value, d.value
+
     def Validate(self):
         """SolutionValidator(graph, solver).Validate() on the device (mcf_validate).  Returns (failed-check bits, primal, dual);
         bits == 0 is `IsValid`."""
