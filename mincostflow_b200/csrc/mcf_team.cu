@@ -38,7 +38,8 @@ namespace {
 
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
-constexpr int kPf = kStageMax / kTT;                    // arcs per pricer thread in the staged block
+constexpr int kStagePos = kStageMax + 16;                // staging positions: the block plus alignment gaps
+constexpr int kPos = (kStagePos + kTT - 1) / kTT;       // positions per pricer thread
 constexpr int kRepEnt = 4;                              // replicas of the ENTER record: a reader polls replica (cta % kRepEnt)
 constexpr int kRepCyc = 4;                              // replicas of every CYC record
 constexpr int kRelUnroll = 4;                           // nodes per thread in flight in the relabel pass
@@ -69,6 +70,10 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -145,8 +150,9 @@ struct TeamShared {
     Book bk;
     Cand cl[kCandCap];              // cycle-node candidates of this slice (owner scan)
     Cand wc[2][kTW];                // per-warp winners (CYC gather, owner slow path)
-    PWin pw[kTW];                   // per-warp pricing winners
-    PWin win;                       // entering arc of this pivot (pricer)
+    longlong2 pk[kTW];              // per-warp pricing winners: {reduced cost, position}
+    Ent win;                        // entering arc of this pivot (pricer)
+    int patch[4];                   // pricer: the two arc-state changes of this pivot
     int4 ent[5];                    // ENTER record as received (owners): words 0-3 the entering arc, word 4 the staging request
     int ncand, abort, cnt, mode, dpF, dpS, ovf;
 };
@@ -245,13 +251,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const pd_s = sz_s + P.slice;
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
     // pricer: arc data and both ends' node records of the staged block [pf_next, pf_next + pf_B)
-    long long* const pf_up = reinterpret_cast<long long*>(body);
-    long long* const pf_rcb = pf_up + kStageMax;                                // cost + pi_s - pi_t as of the basis the records were served from
-    int2* const pf_lab = reinterpret_cast<int2*>(pf_rcb + kStageMax);           // {in[src], in[tgt]} as of the same basis
-    int* const pf_src = reinterpret_cast<int*>(pf_lab + kStageMax);
-    int* const pf_tgt = pf_src + kStageMax;
-    int* const pf_cost = pf_tgt + kStageMax;
-    int* const pf_st = pf_cost + kStageMax;
+    long long* const pf_up = reinterpret_cast<long long*>(body);               // capacity
+    long long* const pf_rcb = pf_up + kStagePos;                                // cost + pi_s - pi_t as of the basis the records were served from
+    long long* const pf_key = pf_rcb + kStagePos;                               // state * that: what the pricing loop compares
+    int2* const pf_lab = reinterpret_cast<int2*>(pf_key + kStagePos);           // {in[src], in[tgt]} as of the same basis
+    int* const pf_src = reinterpret_cast<int*>(pf_lab + kStagePos);
+    int* const pf_tgt = pf_src + kStagePos;
+    int* const pf_st = pf_tgt + kStagePos;
 
     int status = ST_NOT_SOLVED;
     {
@@ -269,11 +275,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (__syncthreads_or(bad)) { if (tid == 0) sh.ovf = 1; }                // reported with CYC(1): the host re-runs wide
         __syncthreads();
     }
-    if (tid == 0) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
+    if (tid == kTT - 32) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
 
     long long iterations = 0;
-#define PROBE(i) do { if (tid == 0 && ((i) < 8 ? cta == 0 : cta == 1)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
-#define TICK(acc) do { if (cta == 0 && tid == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
+    // statistics and phase timers are kept by ONE thread of the last warp of CTA 0 (pricer: slots 0-7) and CTA 1 (first owner: 8-15):
+    // it polls nothing and posts nothing, so that reading the clock never sits in front of a message
+    const bool probe_thr = tid == kTT - 32 && cta <= 1;
+    int cons_low = 0, cons_high = 0;                     // pricer: adaptive block size counters (NS.cs:1399-1438)
+#define PROBE(i) do { if (probe_thr && ((i) < 8) == (cta == 0)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
+#define TICK(acc) do { if (probe_thr && cta == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
 
     // closed-form re-labelling of one node by the update described in `U` (UpdateTreeStructure seen through in[] / depth):
     // nodes of the re-hung subtree [a, a+s) get their new place under v_in, nodes between the old and new place shift by s
@@ -379,7 +389,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         if (has2 && w2.d <= delta) { delta = w2.d; result = 2; }
         const bool change = result != 0;
         if (!change && delta == 0) return ST_UNBOUNDED;                             // NS.cs:321-325
-        if (tid == 0) { if (delta == 0) sh.bk.degenerate++; sh.bk.cycle_nodes += cnt; if (cnt > sh.bk.max_cycle) sh.bk.max_cycle = cnt; }
+        if (probe_thr) { if (delta == 0) sh.bk.degenerate++; sh.bk.cycle_nodes += cnt; if (cnt > sh.bk.max_cycle) sh.bk.max_cycle = cnt; }
         const Cand out = result == 1 ? w1 : w2;
         const bool in_side1 = result == 1;
         const int u_in = in_side1 ? first : second;                                 // NS.cs:999-1008
@@ -397,7 +407,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // ---- STEM(k) (26 % of pivots): the stem is longer than one node; its owners publish the entries, index = depth
         if (ns > 1) {
             int4* const stem_g = P.stemseg + (size_t)par * (n + 1) * 2;             // entry of stem index k at slot t = ns-1-k
-            if (tid == 0) sh.bk.stem_x++;
+            if (probe_thr) sh.bk.stem_x++;
             if constexpr (!kPricer) {
                 auto publish = [&](int j, int in_u, int sz_u, int pd, int dp, bool hasF) {
                     const long long fl = D.new_flow((long long)fl_s[j], pd, hasF, lower_state);
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             }
             TICK(t_stem);
         }
-        if (change && tid == 0) { if (ns > sh.bk.max_stem) sh.bk.max_stem = ns; sh.bk.moved_nodes += s; }
+        if (change && probe_thr) { if (ns > sh.bk.max_stem) sh.bk.max_stem = ns; sh.bk.moved_nodes += s; }
         U.valid = 1; U.change = change ? 1 : 0; U.a = a; U.s = s; U.b = b; U.ns = ns; U.longstem = longstem ? 1 : 0;
         U.dshift = dp_vin + 1 - dp_uin; U.par = par; U.seq = seq;
         U.sigma = D.dir_new_up ? -E.rcb : E.rcb;     // pi[v_in] - pi[u_in] -/+ cost (NS.cs:1187-1188), u_in being the source or the target
@@ -444,54 +454,76 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // ========================================================================================== the pricing CTA
         // BlockSearchPivot fields (NS.cs:1294-1302)
         int next_arc = 0, B = P.block_size;
-        int pf_next = -1, pf_B = 0;                      // what is staged: block [pf_next, pf_next + pf_B) ...
-        long long pf_upto = 0;                           // ... with node records as of "all updates of pivots <= pf_upto applied"
         int ticket = 0;                                  // last staging request issued
-        unsigned pf_missing = 0;                         // bit j: record pair of arc (tid + j * kTT) of the staged block not yet collected
+        // what is staged in shared memory: block [sg_cursor, sg_cursor + sg_cnt) of the arc arrays, laid out in POSITIONS so that every
+        // array is copied as aligned 128-bit words: piece 1 = arcs up to the end of the arrays at positions d0 .., piece 2 (after the
+        // wrap) at positions p2 ..; positions that hold no arc of the block are neutral (state 0)
+        int sg_cursor = -1, sg_cnt = 0, sg_d0 = 0, sg_n1 = 0, sg_p2 = 0, sg_pt = 0;
+        long long sg_upto = -1;                          // the node records are as of "all updates of pivots <= sg_upto applied"
+        unsigned pf_missing = 0;                         // bit j: node records of position (tid + j * kTT) not yet collected
         Pending Uprev;                                   // the previous pivot's update, replayed on the staged node records
         Uprev.valid = Uprev.change = Uprev.a = Uprev.s = Uprev.b = Uprev.longstem = Uprev.dshift = Uprev.par = Uprev.seq = 0; Uprev.ns = 1; Uprev.sigma = 0;
 
-        // stage the arc data of block [cursor, cursor + cnt): src / tgt / cost / capacity are immutable and go global -> shared with
-        // cp.async; `state` is mutable (this CTA is its only writer) and is read around L1 by stage_static_finish()
-        auto stage_static_begin = [&](int cursor, int cnt) {
-#pragma unroll
-            for (int j = 0; j < kPf; ++j) {
-                const int q = tid + j * kTT;
-                if (q < cnt) {
-                    int idx = cursor + q; if (idx >= S) idx -= S;
-                    cp_async4(pf_src + q, P.src + idx); cp_async4(pf_tgt + q, P.tgt + idx); cp_async4(pf_cost + q, P.cost + idx);
-                    cp_async8(pf_up + q, P.upper + idx);
-                }
+        auto layout = [&](int cursor, int cnt) {
+            sg_cursor = cursor; sg_cnt = cnt; sg_d0 = cursor & 3; sg_n1 = min(cnt, S - cursor);
+            sg_p2 = (sg_d0 + sg_n1 + 3) & ~3;
+            sg_pt = cnt > sg_n1 ? sg_p2 + ((cnt - sg_n1 + 3) & ~3) : sg_p2;
+        };
+        auto pos_valid = [&](int p) -> bool { return p < sg_p2 ? (unsigned)(p - sg_d0) < (unsigned)sg_n1 : p - sg_p2 < sg_cnt - sg_n1; };
+        auto pos_arc = [&](int p) -> int { return p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2; };
+        // stage the arc data of the block: src / tgt / capacity are immutable and go global -> shared with 16-byte cp.async;
+        // `state` is mutable (this CTA is its only writer) and is read around L1 by stage_finish().  Threads [t0, kTT) take part.
+        auto stage_begin = [&](int t0) {
+            for (int c = tid - t0; c < (sg_pt >> 2); c += kTT - t0) {
+                const int p = 4 * c;
+                const int g = p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2;
+                cp_async16(pf_src + p, P.src + g); cp_async16(pf_tgt + p, P.tgt + g);
+                cp_async16(pf_up + p, P.upper + g); cp_async16(pf_up + p + 2, P.upper + g + 2);
             }
         };
-        auto stage_static_finish = [&](int cursor, int cnt) {
-#pragma unroll
-            for (int j = 0; j < kPf; ++j) { const int q = tid + j * kTT; if (q < cnt) { int idx = cursor + q; if (idx >= S) idx -= S; pf_st[q] = __ldcg(P.state + idx); } }
+        auto stage_finish = [&]() {
+            for (int c = tid; c < (sg_pt >> 2); c += kTT) {
+                const int p = 4 * c;
+                const int g = p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2;
+                int4 v = __ldcg(reinterpret_cast<const int4*>(P.state + g));
+                if (!pos_valid(p)) v.x = 0; if (!pos_valid(p + 1)) v.y = 0; if (!pos_valid(p + 2)) v.z = 0; if (!pos_valid(p + 3)) v.w = 0;
+                *reinterpret_cast<int4*>(pf_st + p) = v;
+            }
             cp_async_wait_all();
+            __syncthreads();                                            // states and arc data are visible to every thread
         };
-        // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage[]" (word 5 of the ENTER line)
+        // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage[]" (word 4 of the ENTER line)
         auto post_request = [&](int par, int seq, int cursor, int cnt, int tk) {
             if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 4, make_int4(cursor, cnt, tk, seq));
         };
-        auto arm_collect = [&](int cnt) {
+        auto arm_collect = [&]() {
             pf_missing = 0;
 #pragma unroll
-            for (int j = 0; j < kPf; ++j) if (tid + j * kTT < cnt) pf_missing |= 1u << j;
+            for (int j = 0; j < kPos; ++j) {
+                const int p = tid + j * kTT;
+                if (p < sg_pt) {
+                    if (pos_valid(p)) pf_missing |= 1u << j;
+                    else { pf_key[p] = 0; pf_rcb[p] = 0; pf_lab[p] = make_int2(0, 0); }      // label 0 (the root's) is never inside a re-hung interval
+                }
+            }
         };
-        // collect the served node records of the staged block into shared memory; `block`: spin until complete.  True when complete.
+        // collect the served node records of the staged block into shared memory: reduced-cost base, pricing key, labels.
+        // `block`: spin until complete.  True when complete.
         auto collect_staged = [&](int tk, bool block) -> bool {
             unsigned spins = 0; long long t0 = 0;
             for (;;) {
 #pragma unroll
-                for (int jb = 0; jb < kPf; jb += 2) {                    // two record pairs in flight
-                    int4 vs[2], vt[2];
+                for (int jb = 0; jb < kPos; jb += 3) {                   // three record pairs in flight
+                    int4 vs[3], vt[3];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) if (pf_missing >> (jb + j) & 1u) { const int q = tid + (jb + j) * kTT; vs[j] = ld_mail(P.stage + 2 * q); vt[j] = ld_mail(P.stage + 2 * q + 1); }
+                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (pf_missing >> (jb + j) & 1u)) { const int q = tid + (jb + j) * kTT; vs[j] = ld_mail(P.stage + 2 * q); vt[j] = ld_mail(P.stage + 2 * q + 1); }
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) if (pf_missing >> (jb + j) & 1u) {
+                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (pf_missing >> (jb + j) & 1u)) {
                         const int q = tid + (jb + j) * kTT;
                         if (vs[j].w == tk && vt[j].w == tk) {
-                            pf_rcb[q] = (long long)pf_cost[q] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            const long long r = (long long)__ldg(P.cost + pos_arc(q)) + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            const int st = pf_st[q];
+                            pf_rcb[q] = r; pf_key[q] = st > 0 ? r : (st < 0 ? -r : 0);
                             pf_lab[q] = make_int2(vs[j].z, vt[j].z);
                             pf_missing &= ~(1u << (jb + j));
                         }
@@ -508,214 +540,173 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const long long k = iterations + 1;
             const int seq = (int)(unsigned)k;
             const int par = (int)(k & 1);
-            bool have_win = false;
             TICK(t_wdone);
-            if (tid == 0) sh.bk.pr_mark = (unsigned long long)clock64();
+            if (probe_thr) sh.bk.pr_mark = (unsigned long long)clock64();
             // ================================================================ FindEnteringArc (NS.cs:1339-1397), post ENTER(k)
-            const int blk0 = B < S ? B : S;
-            int search_end = 0;
-            if (!(pf_next == next_arc && pf_B == blk0 && pf_upto >= k - 2)) {
-                // nothing usable staged (first pivot): request the first block explicitly and wait for it
-                ++ticket;
-                post_request(par, seq, next_arc, blk0, ticket);
-                stage_static_begin(next_arc, blk0);
-                arm_collect(blk0);
-                stage_static_finish(next_arc, blk0);
-                if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                pf_next = next_arc; pf_B = blk0; pf_upto = k - 1;
-            }
-            // ---- round 0: the first block, from shared memory.  Its node records were served BEFORE the previous pivot's update was
-            // applied (pf_upto == k - 2); that one update is replayed here from its closed form, so pricing waits for nobody.
-            {
-                const bool replay = pf_upto < k - 1 && Uprev.change;
+            // Round r prices block r of the scan, offsets [r * B, (r + 1) * B) from the cursor.  Round 0 is staged already: its node
+            // records were served BEFORE the previous pivot's update was applied (sg_upto == k - 2); that one update is replayed from its
+            // closed form, so pricing waits for nobody.  Later rounds (3-4 % of the pivots) are requested, staged and priced the same way.
+            int win_p = -1, search_end = 0;
+            for (int r = 0;; ++r) {
+                const long long o_lo = (long long)r * B;
+                if (r > 0 && o_lo >= S) { search_end = S; break; }
+                const int cnt = (int)min((long long)B, (long long)S - o_lo);
+                int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
+                if (!(sg_cursor == cur && sg_cnt == cnt && sg_upto >= k - 2)) {
+                    ++ticket;
+                    __syncthreads();                                        // the staging area is no longer read
+                    layout(cur, cnt);
+                    post_request(par, seq, cur, cnt, ticket);
+                    stage_begin(0); arm_collect(); stage_finish();
+                    if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    sg_upto = k - 1;
+                    if (probe_thr && r > 0) sh.bk.rounds_total++;
+                }
+                const bool replay = sg_upto < k - 1 && Uprev.change;
                 const unsigned ra = replay ? (unsigned)Uprev.a : 0u, rs = replay ? (unsigned)Uprev.s : 0u;   // rs == 0: nothing matches
-                const long long sg = Uprev.sigma;
-                long long b_rc = 0;
-                int bq = -1;
-                for (int q = tid; q < blk0; q += kTT) {
-                    const int st = pf_st[q];
-                    const int2 lab = pf_lab[q];
-                    long long v = pf_rcb[q];
-                    // UpdatePotentials of the pending pivot (NS.cs:1185-1209): pi += sigma inside the re-hung interval
-                    if ((unsigned)lab.x - ra < rs) v += sg;
-                    if ((unsigned)lab.y - ra < rs) v -= sg;
-                    const long long rc = st > 0 ? v : (st < 0 ? -v : 0);
-                    if (rc < b_rc) { b_rc = rc; bq = q; }
-                }
-                const int wl = warp_argmin(bq >= 0, b_rc, bq);
-                if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
-                else if (lane == wl) {
-                    PWin best;
-                    best.rc = b_rc; best.off = bq; best.state = pf_st[bq]; best.blk = 0;
-                    int idx = next_arc + bq; if (idx >= S) idx -= S;
-                    best.arc = idx;
-                    best.src = pf_src[bq]; best.tgt = pf_tgt[bq]; best.upper = pf_up[bq];
-                    const int2 lab = pf_lab[bq];
-                    best.in_s = lab.x; best.in_t = lab.y;
-                    best.rcb = best.state > 0 ? b_rc : -b_rc;
-                    if (replay) {                                        // the winner's labels as they are after the pending update
-                        int nx, nd;
-                        relabel(Uprev, best.in_s, 0, nx, nd); best.in_s = nx;
-                        relabel(Uprev, best.in_t, 0, nx, nd); best.in_t = nx;
+                long long bk = 0;
+                int bp = -1;
+                for (int i = tid; i < (sg_pt >> 1); i += kTT) {              // two positions per 128-bit shared-memory load
+                    const longlong2 kk = reinterpret_cast<const longlong2*>(pf_key)[i];
+                    const int4 ll = reinterpret_cast<const int4*>(pf_lab)[i];
+                    long long v0 = kk.x, v1 = kk.y;
+                    // UpdatePotentials of the pending pivot (NS.cs:1185-1209): pi += sigma inside the re-hung interval (rare)
+                    if (((unsigned)ll.x - ra < rs) | ((unsigned)ll.y - ra < rs)) {
+                        long long v = pf_rcb[2 * i]; const int st = pf_st[2 * i];
+                        if ((unsigned)ll.x - ra < rs) v += Uprev.sigma;
+                        if ((unsigned)ll.y - ra < rs) v -= Uprev.sigma;
+                        v0 = st > 0 ? v : (st < 0 ? -v : 0);
                     }
-                    sh.pw[warp] = best;
+                    if (((unsigned)ll.z - ra < rs) | ((unsigned)ll.w - ra < rs)) {
+                        long long v = pf_rcb[2 * i + 1]; const int st = pf_st[2 * i + 1];
+                        if ((unsigned)ll.z - ra < rs) v += Uprev.sigma;
+                        if ((unsigned)ll.w - ra < rs) v -= Uprev.sigma;
+                        v1 = st > 0 ? v : (st < 0 ? -v : 0);
+                    }
+                    if (v0 < bk) { bk = v0; bp = 2 * i; }
+                    if (v1 < bk) { bk = v1; bp = 2 * i + 1; }
                 }
+                const int wl = warp_argmin(bp >= 0, bk, bp);                 // positions ascend with the scan offset: lowest position = first in scan order
+                if (lane == 0) sh.pk[warp] = make_longlong2(0, -1);
+                __syncwarp();
+                if (wl >= 0 && lane == wl) sh.pk[warp] = make_longlong2(bk, bp);
                 __syncthreads();
                 if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                const PWin* qv = &sh.pw[lane & (kTW - 1)];                // every warp: CTA arg-min of (rc, off) over the warp winners
-                const int ww = warp_argmin(lane < kTW && qv->off >= 0, qv->rc, qv->off);
-                if (ww >= 0) { have_win = true; search_end = blk0; if (tid == 0) sh.win = sh.pw[ww]; }
-            }
-            PROBE(0);
-            if (!have_win && blk0 < S) [[unlikely]] {
-                // ---- later rounds: M consecutive blocks per round straight from global memory; their node records are requested
-                // from the owners (who hold the basis as of update k-1: no replay).  The lowest block with a negative reduced cost
-                // wins, inside it the smallest reduced cost, then the first in scan order.
-                const int nblk = (S + B - 1) / B;
-                int next_blk = 1;
-                int found_blk = -1;
-                for (int r = 1; found_blk < 0 && next_blk < nblk; ++r) {
-                    const int mcap = max(1, kReqMax / B);
-                    const int M = min(mcap, r < 2 ? 2 : 8);
-                    const int b_lo = next_blk, b_hi = min(nblk, b_lo + M);
-                    const long long o_lo = (long long)b_lo * B; long long o_hi = (long long)b_hi * B; if (o_hi > S) o_hi = S;
-                    const int cnt = (int)(o_hi - o_lo);
-                    int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
-                    ++ticket;
-                    __syncthreads();                                    // sh.pw of the previous round is consumed
-                    post_request(par, seq, cur, cnt, ticket);
-                    PWin best = pwin_none();
-                    unsigned spins = 0; long long t0 = 0;
-                    for (int off = tid; off < cnt; off += kTT) {
-                        const int blk = b_lo + off / B;
-                        if (best.off >= 0 && blk > best.blk) break;     // a thread's offsets ascend: later blocks cannot win
-                        int idx = cur + off; if (idx >= S) idx -= S;
-                        const int s = __ldg(P.src + idx), t = __ldg(P.tgt + idx), c = __ldg(P.cost + idx);
-                        const int st = __ldcg(P.state + idx);
-                        int4 vs, vt;
-                        for (;;) {
-                            vs = ld_mail(P.stage + 2 * off); vt = ld_mail(P.stage + 2 * off + 1);
-                            if (vs.w == ticket && vt.w == ticket) break;
-                            if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                        }
-                        const long long v = (long long)c + mk64(vs.x, vs.y) - mk64(vt.x, vt.y);
-                        const long long rc = st > 0 ? v : (st < 0 ? -v : 0);
-                        if (rc < best.rc) {
-                            best.rc = rc; best.off = (int)o_lo + off; best.blk = blk; best.arc = idx; best.src = s; best.tgt = t; best.state = st;
-                            best.in_s = vs.z; best.in_t = vt.z; best.rcb = v;
-                        }
-                    }
-                    {   // lowest block first, then (rc, off)
-                        const int mb = __reduce_min_sync(0xffffffffu, best.off >= 0 ? best.blk : INT_MAX);
-                        const int wl = warp_argmin(best.off >= 0 && best.blk == mb, best.rc, best.off);
-                        if (wl < 0) { if (lane == 0) sh.pw[warp].off = -1; }
-                        else if (lane == wl) { best.upper = __ldg(P.upper + best.arc); sh.pw[warp] = best; }
-                    }
-                    __syncthreads();
-                    if (sh.abort) break;
-                    {
-                        const PWin* q = &sh.pw[lane & (kTW - 1)];
-                        const bool qv = lane < kTW && q->off >= 0;
-                        const int mb = __reduce_min_sync(0xffffffffu, qv ? q->blk : INT_MAX);
-                        const int ww = warp_argmin(qv && q->blk == mb, q->rc, q->off);
-                        if (ww >= 0) { found_blk = sh.pw[ww].blk; if (tid == 0) sh.win = sh.pw[ww]; }
-                    }
-                    if (tid == 0) sh.bk.rounds_total++;
-                    next_blk = b_hi;
+                {
+                    const longlong2 q = sh.pk[lane & (kTW - 1)];             // every warp: CTA arg-min of (rc, position) over the warp winners
+                    const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);
+                    if (ww >= 0) win_p = (int)sh.pk[ww].y;
                 }
-                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                if (found_blk >= 0) {
-                    long long e = ((long long)found_blk + 1) * B; if (e > S) e = S;
-                    search_end = (int)e; have_win = true;
-                } else search_end = S;
-            } else if (!have_win) search_end = S;
-            PROBE(6);
+                if (win_p >= 0) { search_end = (int)min(o_lo + B, (long long)S); break; }
+                if (cnt >= S) { search_end = S; break; }
+            }
+            if (status == ST_ERR_BARRIER_TIMEOUT) break;
+            const bool have_win = win_p >= 0;
+            PROBE(0);
+            // the winner's raw fields, read by every thread before the staging area is reused
+            int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0;
+            long long w_up = 0, w_rcb = 0;
+            const bool w_replay = sg_upto < k - 1 && Uprev.change;
+            if (have_win) {
+                w_arc = pos_arc(win_p); w_src = pf_src[win_p]; w_tgt = pf_tgt[win_p]; w_st = pf_st[win_p]; w_up = pf_up[win_p]; w_rcb = pf_rcb[win_p];
+                const int2 lab = pf_lab[win_p]; w_ins = lab.x; w_int = lab.y;
+            }
             // NS.cs:1397-1438: cursor, counters, adaptive block size
-            if (tid == 0) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
-            int cons_low_new = 0, cons_high_new = 0;
+            if (probe_thr) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
             if (have_win) {
                 const int Bold = B;
                 if (P.adaptive) {
                     const double hit = search_end > 0 ? 1.0 / search_end : 0;
-                    int cl = sh.bk.cons_low, ch = sh.bk.cons_high;
                     if (hit < P.low_thr) {
-                        ch = 0; cl++;
-                        if (cl >= P.consecutive) { const int ns = (int)(B * P.shrink); B = P.dyn_min_block > ns ? P.dyn_min_block : ns; cl = 0; }
+                        cons_high = 0; cons_low++;
+                        if (cons_low >= P.consecutive) { const int ns = (int)(B * P.shrink); B = P.dyn_min_block > ns ? P.dyn_min_block : ns; cons_low = 0; }
                     } else if (hit > P.high_thr) {
-                        cl = 0; ch++;
-                        if (ch >= P.consecutive) { const int ns = (int)(B * P.grow); B = P.max_block_size < ns ? P.max_block_size : ns; ch = 0; }
-                    } else { cl = 0; ch = 0; }
-                    cons_low_new = cl; cons_high_new = ch;
+                        cons_low = 0; cons_high++;
+                        if (cons_high >= P.consecutive) { const int ns = (int)(B * P.grow); B = P.max_block_size < ns ? P.max_block_size : ns; cons_high = 0; }
+                    } else { cons_low = 0; cons_high = 0; }
                 }
                 // `_nextArc = e` (NS.cs:1397): the last arc examined, or unchanged after a full sweep that ended inside a block
                 if (search_end < S || S % Bold == 0) { int e = next_arc + search_end - 1; if (e >= S) e -= S; next_arc = e; }
             }
-            __syncthreads();                                            // sh.win is written; cons_low / cons_high were read
-            if (tid == 0 && P.adaptive && have_win) { sh.bk.cons_low = cons_low_new; sh.bk.cons_high = cons_high_new; }
-            // ---- post ENTER(k) (+ the request for the next pivot's block: exactly known now)
             const int nb0 = B < S ? B : S;
             if (have_win) ++ticket;
-            if (warp == 0 && lane < 5 * kRepEnt) {
-                const PWin& w = sh.win;
-                const int wd = lane % 5;
-                int4 o;
-                if (!have_win) o = make_int4(-1, 0, 0, seq);
-                else if (wd == 0) o = make_int4(w.arc, w.src, w.tgt, seq);
-                else if (wd == 1) o = make_int4(w.state, w.in_s, w.in_t, seq);
-                else if (wd == 2) o = make_int4(lo32(w.rcb), hi32(w.rcb), 0, seq);
-                else if (wd == 3) o = make_int4(lo32(w.upper), hi32(w.upper), 0, seq);
-                else o = make_int4(next_arc, nb0, ticket, seq);
-                if (have_win || wd < 4) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 5) * kMailWords + wd, o);
+            __syncthreads();                                                // every thread has read the winner: the staging area is free
+            if (warp == 0) {
+                // ---- warp 0 (all lanes the same values): replay the pending update on the winner, post ENTER(k) + the request for
+                // the next pivot's block, which is exactly known now
+                if (have_win && w_replay) {
+                    if ((unsigned)(w_ins - Uprev.a) < (unsigned)Uprev.s) w_rcb += Uprev.sigma;
+                    if ((unsigned)(w_int - Uprev.a) < (unsigned)Uprev.s) w_rcb -= Uprev.sigma;
+                    int nx, nd;
+                    relabel(Uprev, w_ins, 0, nx, nd); w_ins = nx;
+                    relabel(Uprev, w_int, 0, nx, nd); w_int = nx;
+                }
+                if (lane < 5 * kRepEnt) {
+                    const int wd = lane % 5;
+                    int4 o;
+                    if (!have_win) o = make_int4(-1, 0, 0, seq);
+                    else if (wd == 0) o = make_int4(w_arc, w_src, w_tgt, seq);
+                    else if (wd == 1) o = make_int4(w_st, w_ins, w_int, seq);
+                    else if (wd == 2) o = make_int4(lo32(w_rcb), hi32(w_rcb), 0, seq);
+                    else if (wd == 3) o = make_int4(lo32(w_up), hi32(w_up), 0, seq);
+                    else o = make_int4(next_arc, nb0, ticket, seq);
+                    if (have_win || wd < 4) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 5) * kMailWords + wd, o);
+                }
+                if (lane == 0) { Ent e; e.arc = w_arc; e.src = w_src; e.tgt = w_tgt; e.state = w_st; e.in_s = w_ins; e.in_t = w_int; e.upper = w_up; e.rcb = w_rcb; sh.win = e; }
             }
-            TICK(t_price);
-            PROBE(1);
             if (!have_win) { status = ST_OPTIMAL; break; }
             iterations = k;
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
-            // arc data of the next block streams from DRAM now; the block after it is pulled into L2 (the owners read its ends too)
-            stage_static_begin(next_arc, nb0);
-            arm_collect(nb0);
-            if (nb0 < S) {
-                int c2 = next_arc + nb0 - 1; if (c2 >= S) c2 -= S;
-                for (int q = tid * 32; q < nb0; q += kTT * 32) {
-                    int idx = c2 + q; if (idx >= S) idx -= S;
-                    prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
-                    prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
+            // ---- the other warps meanwhile: arc data of the next block streams from DRAM; the block after it is pulled into L2
+            layout(next_arc, nb0);
+            sg_upto = k - 1;
+            if (warp > 0) {
+                stage_begin(32);
+                if (nb0 < S) {
+                    int c2 = next_arc + nb0 - 1; if (c2 >= S) c2 -= S;
+                    for (int q = (tid - 32) * 32; q < nb0; q += (kTT - 32) * 32) {
+                        int idx = c2 + q; if (idx >= S) idx -= S;
+                        prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
+                        prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
+                    }
                 }
             }
+            arm_collect();
+            TICK(t_price);
+            PROBE(1);
+            // while the owners scan: finish the arc data of the next block, collect its node records (served before the scan)
+            stage_finish();
             PROBE(2);
-            Ent E;
-            {
-                const PWin& w = sh.win;
-                E.arc = w.arc; E.src = w.src; E.tgt = w.tgt; E.state = w.state; E.in_s = w.in_s; E.in_t = w.in_t;
-                E.upper = w.upper; E.rcb = w.rcb;
-            }
-            // off the critical path: finish the arc data of the next block, a first look at the served node records
-            stage_static_finish(next_arc, nb0);
-            collect_staged(ticket, false);
+            if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            const Ent E = sh.win;                                           // (complete: barriers in between)
             PROBE(3);
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<true>(seq, par, E, 0, D, U);
             if (rcd != 0) { status = rcd; break; }
             // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them - state[] in global memory and, when the arc
-            // lies in the block staged for the next pivot, its copy in shared memory (staged before this decision)
+            // lies in the block staged for the next pivot, its copy (and pricing key) in shared memory, staged before this decision
             if (tid == 0) {
                 const int arc0 = E.arc, st0 = D.change ? STATE_TREE : -E.state;
                 const int arc1 = D.change ? D.out.pd >> 1 : -1, st1 = (D.out.zero & 1) ? STATE_LOWER : STATE_UPPER;
                 P.state[arc0] = st0;
-                int q0 = arc0 - next_arc; if (q0 < 0) q0 += S;
-                if (q0 < nb0) pf_st[q0] = st0;
-                if (arc1 >= 0) {
-                    P.state[arc1] = st1;
-                    int q1 = arc1 - next_arc; if (q1 < 0) q1 += S;
-                    if (q1 < nb0) pf_st[q1] = st1;
-                }
+                sh.patch[0] = arc0; sh.patch[1] = st0; sh.patch[2] = arc1; sh.patch[3] = st1;
+                if (arc1 >= 0) P.state[arc1] = st1;
             }
             Uprev = U;                                                              // replayed by the next pricing (see above)
             PROBE(5);
-            // the served node records of the next block: whatever had not arrived before the CYC gather
-            if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-            pf_next = next_arc; pf_B = nb0; pf_upto = k - 1;
+            __syncthreads();
+            if (tid < 2) {                                                          // the two arcs whose state this pivot changed, if staged
+                const int arc = sh.patch[2 * tid], st = sh.patch[2 * tid + 1];
+                if (arc >= 0) {
+                    int off = arc - sg_cursor; if (off < 0) off += S;
+                    if (off < sg_cnt) {
+                        const int p = off < sg_n1 ? sg_d0 + off : sg_p2 + off - sg_n1;
+                        const long long rr = pf_rcb[p];
+                        pf_st[p] = st; pf_key[p] = st > 0 ? rr : (st < 0 ? -rr : 0);
+                    }
+                }
+            }
+            __syncthreads();
             TICK(t_update);
             PROBE(7);
             if (P.stop_after > 0 && iterations >= P.stop_after) { status = ST_STOPPED_EARLY; break; }
@@ -728,7 +719,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // node's record as of the basis this CTA holds right now - into the pricer's staging slots
         auto serve = [&](int cursor, int cnt, int tk) {
             // the range is one or (when it wraps at S) two linear pieces of the arc arrays; each is read as aligned 128-bit words
-            int seg_a = cursor, seg_n = min(cnt, S - cursor), off0 = 0;
+            // (the slots are the pricer's staging positions: piece 1 at d0 .., piece 2 at the next multiple of four)
+            int seg_a = cursor, seg_n = min(cnt, S - cursor), pbase = cursor & 3, done_n = 0;
             for (int piece = 0; piece < 2 && seg_n > 0; ++piece) {
                 const int a0 = seg_a & ~3;
                 const int nch = ((seg_a + seg_n + 3) >> 2) - (a0 >> 2);
@@ -749,14 +741,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             for (int e = 0; e < 4; ++e) {
                                 if ((unsigned)(ob + e) < (unsigned)seg_n) {
                                     const unsigned js = (unsigned)(sv[e] - lo), jt = (unsigned)(tv[e] - lo);
-                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(P.stage + 2 * (off0 + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
-                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(P.stage + 2 * (off0 + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
+                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(P.stage + 2 * (pbase + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
+                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(P.stage + 2 * (pbase + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
                                 }
                             }
                         }
                     }
                 }
-                off0 += seg_n; seg_a = 0; seg_n = cnt - off0;
+                pbase = ((cursor & 3) + seg_n + 3) & ~3;                        // piece 2 starts on a fresh 16-byte boundary of the staging arrays
+                done_n += seg_n; seg_a = 0; seg_n = cnt - done_n;
             }
         };
         for (;;) {
@@ -804,6 +797,26 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (E.arc < 0) { status = ST_OPTIMAL; break; }
             iterations = k;
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
+            // ---- first serve the staging request for the next pivot's block (it came with ENTER(k); the basis this CTA holds is the
+            // one before update k, which is what the pricer will replay update k on): the pricer collects the records while CYC(k) is
+            // in flight, so that its next pricing does not have to wait for them
+            if (!(nreq.w == seq && nreq.z != ticket)) {                  // word 5 had not arrived together with the others: fetch it
+                if (tid == 0) {
+                    int4 v = make_int4(0, 0, 0, 0);
+                    unsigned spins = 0; long long t0 = 0;
+                    for (;;) {
+                        v = ld_mail(line + 4);
+                        if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
+                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                    }
+                    sh.ent[4] = v;
+                }
+                __syncthreads();
+                nreq = sh.ent[4];
+            }
+            if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
+            PROBE(8);
+
             const bool lower_state = E.state == STATE_LOWER;
             const int first = lower_state ? E.src : E.tgt, second = lower_state ? E.tgt : E.src;      // NS.cs:948-957
             const int inF = lower_state ? E.in_s : E.in_t, inS = lower_state ? E.in_t : E.in_s;
@@ -902,25 +915,6 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
             }
             PROBE(11);
-            // ---- off the critical path: serve the staging request for the next pivot's block (it came with ENTER(k); the basis
-            // this CTA holds is the one before update k, which is what the pricer will replay update k on)
-            if (!(nreq.w == seq && nreq.z != ticket)) {                  // word 5 had not arrived together with the others: fetch it
-                if (tid == 0) {
-                    int4 v = make_int4(0, 0, 0, 0);
-                    unsigned spins = 0; long long t0 = 0;
-                    for (;;) {
-                        v = ld_mail(line + 4);
-                        if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
-                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                    }
-                    sh.ent[4] = v;
-                }
-                __syncthreads();
-                nreq = sh.ent[4];
-            }
-            if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
-            PROBE(8);
-
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<false>(seq, par, E, nc, D, U);
             if (rcd != 0) { status = rcd; break; }
@@ -1020,7 +1014,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     }
 #undef TICK
 #undef PROBE
-    if (tid == 0 && (cta == 0 || cta == 1)) for (int i = cta == 0 ? 0 : 8; i < (cta == 0 ? 8 : 16); ++i) P.ctl->clk[i] = sh.bk.pr[i];
+    if (probe_thr) for (int i = cta == 0 ? 0 : 8; i < (cta == 0 ? 8 : 16); ++i) P.ctl->clk[i] = sh.bk.pr[i];
 
     // =================================================================== epilogue
     const bool clean = status != ST_ERR_BARRIER_TIMEOUT;
@@ -1072,7 +1066,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
-constexpr size_t kPricerBytes = (size_t)mcf::kStageMax * (3 * 8 + 4 * 4);   // up, rcb, lab + src, tgt, cost, st
+constexpr size_t kPricerBytes = (size_t)(mcf::kStageMax + 16) * (4 * 8 + 3 * 4);   // up, rcb, key, lab + src, tgt, st
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 
