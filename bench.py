@@ -2,7 +2,8 @@
 """bench.py - BASELINE.json's metric on its own config: one network-simplex solve of NETGEN-8 2^20 nodes / 2^23 arcs
 (Block Search, auto-configuration off = the canonical comparator of SURVEY.md A.3) per step, per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload netgen20|netgen18|netgen16|batch18]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload netgen20|netgen18|netgen16|netgen10k|grid1024|batch18]      (BASELINE.json configs 3, -, 2, 1, 4, 5)
 
 One JSON line on stdout (rank 0).  Keys follow the driver contract:
   value         pivots/s, whole job, device-timed: CUDA events around the persistent pivot kernel on the stream it is launched
@@ -13,7 +14,11 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
   cpu_baseline  the CPU oracle (C restatement of the reference's NetworkSimplex.cs) on a bounded sample of the same workload
   pivot_kernel  in-kernel phase split of the persistent kernel (pricing / cycle / update) and its own pricing GB/s
 N > 1 (torchrun, one rank per GPU): every rank solves its own NETGEN instance of the same size (seed + rank) - a single
-solve is sequential across pivots and does not shard - results are gathered on rank 0 over NCCL.
+solve is sequential across pivots and does not shard - and the full result records {status, pivots, cost,
+flow[m], pi[n]} are gathered on rank 0 over NCCL straight from the engine's device arrays (mincostflow_b200/batch.py).
+Warm-up steps are BOUNDED solves of the same instance (the first 200 000 pivots; `config.warmup_kind`): they warm the
+context, the allocations and the instruction caches, which is all a warm-up does for a solver whose timed step is one
+20-second kernel; timed steps are full solves.
 `--impl reference` times the CPU oracle (oracle/, the restated reference) on the box's host cores instead.
 """
 import argparse
@@ -31,16 +36,34 @@ import numpy as np  # noqa: E402
 
 SEED = 13502460
 WORKLOADS = {
-    # name: (log2 n, instances per rank per step, CPU sample: pivots of the prefix window [0 = the full solve])
-    "netgen20": (20, 1, 600_000),
+    # name: (log2 n or generator tag, instances per rank per step, CPU sample: pivots of the prefix window [0 = the full solve])
+    "netgen20": (20, 1, 600_000),         # BASELINE.json config 3 - the headline
     "netgen18": (18, 1, 300_000),
-    "netgen16": (16, 1, 0),
-    "batch18": (18, 8, 300_000),          # BASELINE.json config 5: 64 instances of 2^18 nodes = 8 per GPU at 8 GPUs
+    "netgen16": (16, 1, 0),               # config 2
+    "netgen10k": ("10k", 1, 0),           # config 1 (NETGEN 10 000 nodes / 30 000 arcs)
+    "grid1024": ("grid", 1, 0),           # config 4 (1024 x 1024 time-expanded grid)
+    "batch18": (18, 8, 300_000),          # config 5: 64 instances of 2^18 nodes = 8 per GPU at 8 GPUs
 }
 MID_WINDOW = {20: 40_000, 18: 100_000}    # pivots timed from each mid-solve checkpoint (oracle/_ref/ckpt_*.npz)
+WARMUP_PIVOTS = 200_000                   # warm-up steps stop after this many pivots
 
 
-def cpu_sample(p, k, prefix):
+class MissingCheckpoints(RuntimeError):
+    pass
+
+
+def host_info():
+    info = {"nproc": os.cpu_count()}
+    try:
+        for ln in subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout.splitlines():
+            if ln.startswith("Model name"):
+                info["cpu_model"] = ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return info
+
+
+def cpu_sample(p, k, prefix, scale=1.0):
     """Times the CPU oracle on a bounded sample of ONE solve of `p`: the first `prefix` pivots and, when the checkpoints
     written by tools/make_checkpoints.py travelled with the repo, a window from each of them (the reference's per-pivot cost
     grows by more than an order of magnitude over a solve; a prefix alone flatters it).  The mean is weighted by how much of
@@ -49,6 +72,7 @@ def cpu_sample(p, k, prefix):
     from oracle import oracle
     cfg = oracle.default_config()
     wins = []
+    prefix = int(prefix * scale)
     r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=prefix)
     wins.append({"from_pivot": 0, "pivots": int(r.iterations), "seconds": r.loop_seconds})
     if prefix == 0:
@@ -56,18 +80,22 @@ def cpu_sample(p, k, prefix):
     ck = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", f"ckpt_{p.name}_*.npz")))
     rec = (recorded_cpu() or {}).get(p.name)
     if not ck or not rec:
-        return r.iterations / r.loop_seconds, f"first {prefix} pivots of one solve (no mid-solve checkpoints present)", wins
+        # a prefix alone flatters the CPU by 2x (its per-pivot cost grows over the solve): no silent fallback
+        raise MissingCheckpoints(f"oracle/_ref/ckpt_{p.name}_*.npz not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 f"(or tools/make_checkpoints.py {k} 0.33,0.66,0.85) once - about 15 CPU-minutes - or pass --no-cpu")
     total = rec["pivots"]
+    mid = max(int(MID_WINDOW[k] * scale), 2000)
     for path in ck:
         st = oracle.State.load(path)
         start = st.iterations
-        r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + MID_WINDOW[k], resume=st)
+        r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + mid, resume=st)
         wins.append({"from_pivot": int(start), "pivots": int(r.iterations - start), "seconds": r.loop_seconds})
-    # the reference itself zero-fills a stackalloc int[n] on every stem re-hang (NetworkSimplex.cs:1085); the port hoists that
-    # scratch (conservative).  One mid-solve window is repeated with the zero-fill, for the record only.
-    st = oracle.State.load(ck[len(ck) // 2]); start = st.iterations
-    r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + MID_WINDOW[k] // 4, resume=st, emulate_stackalloc=True)
-    wins[1 + len(ck) // 2]["us_per_pivot_with_reference_stackalloc"] = 1e6 * r.loop_seconds / max(r.iterations - start, 1)
+    if scale >= 1.0:
+        # the reference itself zero-fills a stackalloc int[n] on every stem re-hang (NetworkSimplex.cs:1085); the port hoists that
+        # scratch (conservative).  One mid-solve window is repeated with the zero-fill, for the record only.
+        st = oracle.State.load(ck[len(ck) // 2]); start = st.iterations
+        r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + mid // 4, resume=st, emulate_stackalloc=True)
+        wins[1 + len(ck) // 2]["us_per_pivot_with_reference_stackalloc"] = 1e6 * r.loop_seconds / max(r.iterations - start, 1)
     # each window stands for the stretch of the solve up to the next window's start
     starts = [w["from_pivot"] for w in wins] + [total]
     est_seconds = sum(w["seconds"] / w["pivots"] * (starts[i + 1] - starts[i]) for i, w in enumerate(wins))
@@ -78,6 +106,10 @@ def cpu_sample(p, k, prefix):
 
 def workload_name(w):
     k, per, _ = WORKLOADS[w]
+    if k == "10k":
+        return f"NETGEN 10000 nodes / 30000 arcs (100 sources, 100 sinks, supply 100000), seed {SEED}+i, Block Search, auto-configuration off"
+    if k == "grid":
+        return "1024 x 1024 time-expanded grid (splitmix64 seed 42+i), Block Search, auto-configuration off"
     return (f"NETGEN-8 2^{k} nodes / 2^{k + 3} arcs, seed {SEED}+i, Block Search, auto-configuration off"
             + (f", {per} instances per GPU per step" if per > 1 else ""))
 
@@ -132,6 +164,10 @@ class ClockSampler:
 def make_instances(workload, rank):
     from mincostflow_b200 import instances
     k, per, _ = WORKLOADS[workload]
+    if k == "10k":
+        return [instances.netgen(SEED + rank, instances.netgen_params(10000, m=30000, sources=100, sinks=100, supply=100000), name="netgen_10k_30k")]
+    if k == "grid":
+        return [instances.grid_time_expanded(1024, 1024, seed=42 + rank)]
     return [instances.netgen8(k, seed=SEED + rank * per + i) for i in range(per)]
 
 
@@ -141,6 +177,22 @@ def measured_peak():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_full_cpu(name):
+    """One FULL solve of the instance by the oracle port and by LEMON 1.3.1, recorded on a B200 box's host (tools/cpu_full_solve.py,
+    profiles/r02_cpu_full_20.json): the yardstick the sampled estimate is checked against."""
+    path = os.path.join(ROOT, "profiles", "r02_cpu_full_20.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        d = json.load(f)
+    if d.get("instance") != name:
+        return {}
+    o = d.get("oracle_port", {}); l = d.get("lemon_1_3_1", {})
+    return {"recorded_full_solve": {"oracle_port_s": o.get("loop_seconds"), "oracle_port_pivots_per_s": o.get("pivots_per_s"),
+                                    "lemon_1_3_1_run_s": l.get("run_seconds"), "pivots": o.get("pivots"), "host": d.get("host"),
+                                    "where": "host cores of a B200 box of this pool, profiles/r02_cpu_full_20.json"}}
 
 
 def recorded_cpu():
@@ -162,9 +214,12 @@ def run_reference(args):
     p = make_instances(args.workload, 0)[0]
     vals, secs = [], []
     sample_txt = ""
+    # every timed step is the same bounded sample of one solve, sized so that the whole run ends within a few minutes:
+    # a quarter of the cpu_baseline sample per step at the driver's 20 steps (warm-up steps: a twentieth; a CPU needs none)
+    scale = min(1.0, 5.0 / max(args.steps, 1))
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        v, sample_txt, wins = cpu_sample(p, k, sample)
+        v, sample_txt, wins = cpu_sample(p, k, sample, scale=scale if it >= args.warmup else 0.05)
         if it >= args.warmup:
             vals.append(v); secs.append(time.perf_counter() - t0)
     value = float(np.mean(vals))
@@ -174,7 +229,8 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
            "config": {"workload": workload_name(args.workload), "sample": sample_txt},
-           "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt},
+           "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt, **host_info(),
+                            **recorded_full_cpu(p.name)},
            "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -214,45 +270,57 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        """One pass of the hot path over this rank's batch; returns (pivots, kernel_us, launches, h2d, d2h, result tensor)."""
+    width = batch.record_width(max(p.m for p in probs), max(p.n for p in probs))
+
+    def step(bounded=False):
+        """One pass of the hot path over this rank's batch; returns (pivots, kernel_us, launches, h2d, d2h).  `bounded`: warm-up."""
         piv = kus = h2d = d2h = 0
         launches = 0
-        res = []
+        for ns in solvers:
+            ns.set_engine_options(stop_after_pivots=WARMUP_PIVOTS if bounded else 0)
+            ns._dirty = True                                   # host buffers are marshalled and uploaded again every step
         if per > 1:                                            # a batch: `args.concurrency` solves side by side on this GPU
-            for ns in solvers:
-                ns._dirty = True
             t0 = time.perf_counter()
             sts = mcf.solve_batch(solvers, [local_rank], per_device=args.concurrency)
             batch_us = (time.perf_counter() - t0) * 1e6
         for i, ns in enumerate(solvers):
-            if per > 1:
-                st = sts[i]
-            else:
-                ns._dirty = True                               # host buffers are marshalled and uploaded again every step
-                st = ns.Solve()
+            st = sts[i] if per > 1 else ns.Solve()
             M = ns.GetMetrics()
-            assert st == mcf.SolverStatus.Optimal, st
+            assert bounded or st == mcf.SolverStatus.Optimal, st
             piv += M.iterations; kus += M.kernel_time_us if per == 1 else 0; h2d += M.h2d_bytes; d2h += M.d2h_bytes; launches += 1
-            res.append(batch.make_record(rank * per + i, int(st), M.iterations, ns.GetTotalCost(), ns.flows(), ns.potentials()))
         if per > 1:
-            kus = batch_us                                     # solves overlap: the device-side figure is the batch's span
-        return piv, kus, launches, h2d, d2h, res
+            kus = batch_us                                     # solves overlap: the figure is the host-timed span of the batch
+        return piv, kus, launches, h2d, d2h
+
+    def gather():
+        """NCCL gather of the full result records {status, pivots, cost, flow[m], pi[n]} on rank 0, packed on the
+        device from the arrays the solves left in HBM.  Returns (milliseconds on this rank, records verified on rank 0)."""
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        buf = batch.new_buffer(per, width, dev)
+        for i, ns in enumerate(solvers):
+            flow, pi = batch.device_result_tensors(ns)
+            batch.pack_record(buf[i], rank * per + i, int(ns.Status), ns.GetMetrics().iterations, ns.GetTotalCost(), flow, pi)
+        got = batch.gather_records(buf, world * per, dist=dist)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            assert all(v["ok"] and v["status"] == 1 for v in got.values()), {i: (v["status"], v["ok"]) for i, v in got.items()}
+        return ms, (len(got) if got is not None else 0)
 
     for _ in range(args.warmup):
-        step()
+        step(bounded=True)
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     t0 = time.perf_counter()
     tot_piv = tot_kus = tot_h2d = tot_d2h = tot_launch = 0
-    last = None
+    gather_ms = 0.0; gathered_n = 0
     for _ in range(args.steps):
-        piv, kus, launches, h2d, d2h, last = step()
+        piv, kus, launches, h2d, d2h = step()
         tot_piv += piv; tot_kus += kus; tot_h2d += h2d; tot_d2h += d2h; tot_launch += launches
-        if dist is not None:                                   # NCCL gather of the result records on rank 0 (SURVEY.md 8e)
-            gathered = batch.gather_records(last, world * per, dist=dist, device=dev)
-            if rank == 0:
-                assert (gathered[:, 1] == 1).all(), gathered
+        if dist is not None:
+            g_ms, gathered_n = gather()
+            gather_ms += g_ms
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -294,11 +362,16 @@ def run_ours(args):
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "instances_per_gpu_per_step": per, "pivots_per_step_rank0": tot_piv // args.steps,
+                   "warmup_kind": f"bounded solves of the same instance (first {WARMUP_PIVOTS} pivots); timed steps are full solves",
+                   "value_timing": "CUDA events around the pivot kernel" if per == 1 else "host wall clock around mcf_solve_batch_concurrent (the solves overlap on the device)",
                    "l2": "inputs larger than L2 (arc arrays 16 B x %d arcs; every step re-uploads them)" % S,
                    "grid_ctas": M.grid_ctas, "pricing_kind": M.pricing_kind, "block_size": M.initial_block_size},
         "solve_ms": {"kernel": kus_max / 1e3 / args.steps / per, "end_to_end": 1e3 * wall / args.steps / per},
         "e2e": {"value": e2e, "unit": "pivots/s", "h2d_bytes_per_step": int(h2d_all / args.steps), "d2h_bytes_per_step": int(d2h_all / args.steps)},
         "gpu_launches": int(launch_all),
+        "result_gather": ({"ms_per_step_rank0": gather_ms / args.steps, "records_on_rank0": gathered_n, "bytes_per_record": 8 * width,
+                           "what": "NCCL gather of {status, pivots, cost, flow[m], pi[n]} from every rank's device arrays; checksums re-verified on rank 0"}
+                          if dist is not None else None),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ns_price_sweep_kernel (Best Eligible full scan, 16 B/arc x S arcs per launch)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -312,11 +385,11 @@ def run_ours(args):
                          "arcs_priced_per_pivot": M.arcs_priced / max(M.iterations, 1),
                          # in-kernel probes of the team engine (clock64 deltas of one pricing CTA and of the first owner CTA), us per pivot
                          "pricer_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
-                             ("price_and_post_ENTER", 1), ("collect_ENTER", 2), ("stage_next_block_arcs", 3), ("wait_DONE", 6), ("finish_staging", 0),
-                             ("gather_node_records_post_GATHERED", 7), ("wait_and_gather_CYC", 4), ("decide", 5))} if M.engine == 2 else None,
+                             ("price_all_rounds", 0), ("cursor_post_ENTER_start_staging", 1), ("collect_node_records_of_next_block", 2),
+                             ("finish_staging", 3), ("wait_and_gather_CYC", 4), ("decide_and_state_update", 5))} if M.engine == 2 else None,
                          "owner_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
-                             ("wait_and_collect_ENTER", 9), ("scan_slice", 10), ("reduce_and_post_CYC", 11), ("gather_CYC_and_decide", 12),
-                             ("cycle_node_update", 15), ("relabel", 13), ("post_DONE", 14))} if M.engine == 2 else None,
+                             ("wait_ENTER", 9), ("scan_slice", 10), ("reduce_and_post_CYC", 11), ("serve_staging_request", 8),
+                             ("gather_CYC_and_decide", 12), ("cycle_node_update", 15), ("relabel", 13), ("end_of_pivot_barrier", 14))} if M.engine == 2 else None,
                          "pricing_GBps_in_kernel": M.pricing_bytes / max(M.pivot_search_time_us, 1e-9) / 1e3},
     }
     # CPU baseline (oracle port) on a bounded sample + the GPU on the very same sample
@@ -325,8 +398,11 @@ def run_ours(args):
         cpu_v, sample_txt, wins = cpu_sample(probs[0], k, sample)
         cpu_s = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": cpu_v, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt + " (same instance)",
-                               "seconds": cpu_s, "windows": wins,
-                               "prefix_only_value": wins[0]["pivots"] / wins[0]["seconds"]}
+                               "seconds": cpu_s, "windows": wins, **host_info(),
+                               "prefix_only_value": wins[0]["pivots"] / wins[0]["seconds"], **recorded_full_cpu(probs[0].name)}
+        full = out["cpu_baseline"].get("recorded_full_solve")
+        if full and full.get("oracle_port_pivots_per_s"):
+            out["cpu_baseline"]["sampling_error_vs_recorded_full_solve"] = cpu_v / full["oracle_port_pivots_per_s"] - 1.0
         if sample:
             ns = solvers[0]
             ns.set_engine_options(stop_after_pivots=sample)
@@ -334,6 +410,7 @@ def run_ours(args):
             t0 = time.perf_counter(); ns.Solve(); gw = time.perf_counter() - t0
             Ms = ns.GetMetrics()
             ns.set_engine_options(stop_after_pivots=0)
+            ns._dirty = True
             out["cpu_baseline"]["gpu_same_sample"] = {"pivots": Ms.iterations, "kernel_pivots_per_s": Ms.iterations / (Ms.kernel_time_us * 1e-6),
                                                       "e2e_pivots_per_s": Ms.iterations / gw}
         rec = recorded_cpu()

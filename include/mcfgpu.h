@@ -173,6 +173,11 @@ int mcf_get_arc_upper_bound(mcf_handle* h, int32_t arc, int64_t* out);
 
 int mcf_get_metrics(mcf_handle* h, mcf_metrics* out);             /* GetMetrics, NetworkSimplex.cs:584 */
 
+/* Bounded solves (mcf_options.stop_after_pivots > 0: samples, tests, warm-up): the arc flows (before the lower-bound restore of
+ * NetworkSimplex.cs:375-388) and node potentials of the basis the solve stopped at, i.e. the solver state after exactly that many
+ * pivots of NetworkSimplex.cs:282-341.  MCF_ERR_NOT_SOLVED unless the last solve ended that way.  Pointers may be NULL. */
+int mcf_get_state_after_stop(mcf_handle* h, int64_t* flow_out_m, int64_t* potential_out_n);
+
 /* The result arrays of the last Optimal solve where the solve left them in HBM (flow[m] in arc-id order, potential[n] in
  * node-id order, both int64) and the device they live on: what GetFlow / GetPotential serve from the host copies.  For the
  * multi-GPU result gather of a batch, which sends the records GPU -> GPU over NCCL without a host bounce.

@@ -71,6 +71,7 @@ struct mcf_handle {
     mcf_options opt{};
     int status = MCF_NOT_SOLVED;
     bool solved_once = false;
+    bool stopped_early = false;                                       // the last solve ended at opt.stop_after_pivots
     std::vector<int64_t> flow, pi;                                    // results, host side
     int64_t total_cost = 0;
     mcf_metrics metrics{};
@@ -451,6 +452,7 @@ int solve_team(mcf_handle* h, int team, int slice, int wide, int block, int dyn_
         return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kTeamStemCap);
     }
     int st;
+    h->stopped_early = ctl.status == mcf::ST_STOPPED_EARLY;
     switch (ctl.status) {
         case mcf::ST_OPTIMAL: st = ctl.infeasible ? MCF_INFEASIBLE : MCF_OPTIMAL; break;             // NS.cs:360-393
         case mcf::ST_INFEASIBLE: st = MCF_INFEASIBLE; break;
@@ -573,6 +575,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     const auto t_total = clk::now();
     h->metrics = mcf_metrics{};
     h->status = MCF_NOT_SOLVED;
+    h->stopped_early = false;
     h->d_pi_final = nullptr;
     const int n = h->n, m = h->m, S = m + n;
     auto done = [&](int st) { h->status = st; h->solved_once = true; if (status_out) *status_out = st; h->metrics.total_solve_time_us = us_since(t_total); return MCF_OK; };
@@ -726,6 +729,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
         return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: cycle/stem exceeds the in-kernel staging buffer (%d / %d entries)", (long long)ctl.iterations, mcf::kListSmem, mcf::kStemCap);
     }
     int st;
+    h->stopped_early = ctl.status == mcf::ST_STOPPED_EARLY;
     switch (ctl.status) {
         case mcf::ST_OPTIMAL: st = ctl.infeasible ? MCF_INFEASIBLE : MCF_OPTIMAL; break;             // NS.cs:360-393
         case mcf::ST_INFEASIBLE: st = MCF_INFEASIBLE; break;
@@ -807,6 +811,15 @@ int mcf_get_metrics(mcf_handle* h, mcf_metrics* out)
     if (!h || !out) return MCF_ERR_INVALID_ARGUMENT;
     if (!h->solved_once) return fail(h, MCF_ERR_NOT_SOLVED, "Solve() has not been called");
     *out = h->metrics; return MCF_OK;
+}
+
+int mcf_get_state_after_stop(mcf_handle* h, int64_t* flow_out, int64_t* potential_out)
+{
+    if (!h) return MCF_ERR_INVALID_ARGUMENT;
+    if (!h->stopped_early) return fail(h, MCF_ERR_NOT_SOLVED, "the last solve did not end at stop_after_pivots");
+    if (flow_out) std::memcpy(flow_out, h->flow.data(), (size_t)h->m * 8);
+    if (potential_out) std::memcpy(potential_out, h->pi.data(), (size_t)h->n * 8);
+    return MCF_OK;
 }
 
 int mcf_get_device_results(mcf_handle* h, const int64_t** flow_dev_out, const int64_t** potential_dev_out, int32_t* device_out)

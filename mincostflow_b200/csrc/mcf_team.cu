@@ -251,11 +251,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const pd_s = sz_s + P.slice;
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
     // pricer: arc data and both ends' node records of the staged block [pf_next, pf_next + pf_B)
-    long long* const pf_up = reinterpret_cast<long long*>(body);               // capacity
-    long long* const pf_rcb = pf_up + kStagePos;                                // cost + pi_s - pi_t as of the basis the records were served from
-    long long* const pf_key = pf_rcb + kStagePos;                               // state * that: what the pricing loop compares
-    int2* const pf_lab = reinterpret_cast<int2*>(pf_key + kStagePos);           // {in[src], in[tgt]} as of the same basis
-    int* const pf_src = reinterpret_cast<int*>(pf_lab + kStagePos);
+    long long* const pf_up = reinterpret_cast<long long*>(dyn_smem);           // capacity (the pricer stages no stems: the whole area is its)
+    long long* const pf_rcb = pf_up + kStagePos;                                // [2] cost + pi_s - pi_t as of the basis the records were served from
+    int2* const pf_lab = reinterpret_cast<int2*>(pf_rcb + 2 * kStagePos);       // [2] {in[src], in[tgt]} as of the same basis
+    int* const pf_src = reinterpret_cast<int*>(pf_lab + 2 * kStagePos);
     int* const pf_tgt = pf_src + kStagePos;
     int* const pf_st = pf_tgt + kStagePos;
 
@@ -431,7 +430,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     }
                 }
             }
-            if (!longstem) {
+            if (!kPricer && !longstem) {
                 for (int q = tid; q < ns; q += kTT) {
                     int4 w[2];
                     if (!poll_rec<2>(stem_g + (size_t)q * 2, seq, w, P)) sh.abort = 1;
@@ -454,15 +453,21 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // ========================================================================================== the pricing CTA
         // BlockSearchPivot fields (NS.cs:1294-1302)
         int next_arc = 0, B = P.block_size;
-        int ticket = 0;                                  // last staging request issued
-        // what is staged in shared memory: block [sg_cursor, sg_cursor + sg_cnt) of the arc arrays, laid out in POSITIONS so that every
-        // array is copied as aligned 128-bit words: piece 1 = arcs up to the end of the arrays at positions d0 .., piece 2 (after the
-        // wrap) at positions p2 ..; positions that hold no arc of the block are neutral (state 0)
-        int sg_cursor = -1, sg_cnt = 0, sg_d0 = 0, sg_n1 = 0, sg_p2 = 0, sg_pt = 0;
-        long long sg_upto = -1;                          // the node records are as of "all updates of pivots <= sg_upto applied"
-        unsigned pf_missing = 0;                         // bit j: node records of position (tid + j * kTT) not yet collected
-        Pending Uprev;                                   // the previous pivot's update, replayed on the staged node records
-        Uprev.valid = Uprev.change = Uprev.a = Uprev.s = Uprev.b = Uprev.longstem = Uprev.dshift = Uprev.par = Uprev.seq = 0; Uprev.ns = 1; Uprev.sigma = 0;
+        int ticket = 0, last_tk = 0;                     // last staging request issued; the one before it
+        // Staging area.  A block [cursor, cursor + cnt) of the arc arrays is laid out in POSITIONS so that every array is copied as
+        // aligned 128-bit words: piece 1 = arcs up to the end of the arrays at positions d0 .., piece 2 (after the wrap) at p2 ..;
+        // positions that hold no arc of the block are neutral (state 0).
+        //   cold part (one copy: src, tgt, capacity, state) - staged with cp.async for the block of the NEXT pivot, exactly known
+        //   hot part (two copies by pivot parity: cost + pi_s - pi_t and both labels) - the node records the owners serve.  The block
+        //   of pivot k+2 is requested with ENTER(k) at its predicted place (the search of pivot k+1 ends in its first block 9 times out
+        //   of 10), served by the owners off their critical path from the basis before update k, collected here one pivot later, and
+        //   priced with updates k and k+1 replayed in closed form.  So in the steady state pricing waits for nobody.
+        int sg_cursor = -1, sg_cnt = 0, sg_d0 = 0, sg_n1 = 0, sg_p2 = 0, sg_pt = 0;     // cold part: which block, its layout
+        int hb_cur[2] = {-1, -1}, hb_cnt[2] = {0, 0}, hb_basis[2] = {0, 0};             // hot copies: which block, as of which basis (low 32 bits of the pivot index)
+        bool hb_ok[2] = {false, false};                                                 // ... and whether its records are in shared memory
+        Pending U1, U2;                                  // the updates of pivots k-2 and k-1, replayed on the staged node records
+        U1.valid = U1.change = U1.a = U1.s = U1.b = U1.longstem = U1.dshift = U1.par = U1.seq = 0; U1.ns = 1; U1.sigma = 0;
+        U2 = U1;
 
         auto layout = [&](int cursor, int cnt) {
             sg_cursor = cursor; sg_cnt = cnt; sg_d0 = cursor & 3; sg_n1 = min(cnt, S - cursor);
@@ -471,8 +476,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         };
         auto pos_valid = [&](int p) -> bool { return p < sg_p2 ? (unsigned)(p - sg_d0) < (unsigned)sg_n1 : p - sg_p2 < sg_cnt - sg_n1; };
         auto pos_arc = [&](int p) -> int { return p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2; };
-        // stage the arc data of the block: src / tgt / capacity are immutable and go global -> shared with 16-byte cp.async;
-        // `state` is mutable (this CTA is its only writer) and is read around L1 by stage_finish().  Threads [t0, kTT) take part.
+        // cold part: src / tgt / capacity are immutable and go global -> shared with 16-byte cp.async; `state` is mutable (this
+        // CTA is its only writer) and is read around L1 by stage_finish().  Threads [t0, kTT) take part in stage_begin.
         auto stage_begin = [&](int t0) {
             for (int c = tid - t0; c < (sg_pt >> 2); c += kTT - t0) {
                 const int p = 4 * c;
@@ -492,97 +497,130 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             cp_async_wait_all();
             __syncthreads();                                            // states and arc data are visible to every thread
         };
-        // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage[]" (word 4 of the ENTER line)
-        auto post_request = [&](int par, int seq, int cursor, int cnt, int tk) {
-            if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 4, make_int4(cursor, cnt, tk, seq));
+        // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage buffer `buf`" (word 4 of the ENTER line)
+        auto post_request = [&](int par, int seq, int cursor, int cnt, int tk, int buf) {
+            if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 4, make_int4(cursor, cnt, tk * 4 + buf, seq));
         };
-        auto arm_collect = [&]() {
-            pf_missing = 0;
+        // collect the served node records of block (cursor, cnt), request `tk` in stage buffer `buf`, into hot copy h: reduced-cost base and
+        // labels per position.  Spins until complete; false = abandoned.
+        auto collect = [&](int h, int cursor, int cnt, int tk, int buf) -> bool {
+            const int d0 = cursor & 3, n1 = min(cnt, S - cursor), p2 = (d0 + n1 + 3) & ~3;
+            const int pt = cnt > n1 ? p2 + ((cnt - n1 + 3) & ~3) : p2;
+            long long* const rcb = pf_rcb + h * kStagePos;
+            int2* const lab = pf_lab + h * kStagePos;
+            const int4* const sbuf = P.stage + (size_t)buf * 2 * kStagePos;
+            const int tkw = tk * 4 + buf;
+            unsigned missing = 0;
 #pragma unroll
             for (int j = 0; j < kPos; ++j) {
                 const int p = tid + j * kTT;
-                if (p < sg_pt) {
-                    if (pos_valid(p)) pf_missing |= 1u << j;
-                    else { pf_key[p] = 0; pf_rcb[p] = 0; pf_lab[p] = make_int2(0, 0); }      // label 0 (the root's) is never inside a re-hung interval
+                if (p < pt) {
+                    const bool valid = p < p2 ? (unsigned)(p - d0) < (unsigned)n1 : p - p2 < cnt - n1;
+                    if (valid) missing |= 1u << j;
+                    else { rcb[p] = 0; lab[p] = make_int2(0, 0); }      // label 0 (the root's) is never inside a re-hung interval
                 }
             }
-        };
-        // collect the served node records of the staged block into shared memory: reduced-cost base, pricing key, labels.
-        // `block`: spin until complete.  True when complete.
-        auto collect_staged = [&](int tk, bool block) -> bool {
             unsigned spins = 0; long long t0 = 0;
             for (;;) {
 #pragma unroll
                 for (int jb = 0; jb < kPos; jb += 3) {                   // three record pairs in flight
                     int4 vs[3], vt[3];
+                    int cs[3];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (pf_missing >> (jb + j) & 1u)) { const int q = tid + (jb + j) * kTT; vs[j] = ld_mail(P.stage + 2 * q); vt[j] = ld_mail(P.stage + 2 * q + 1); }
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (pf_missing >> (jb + j) & 1u)) {
+                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
                         const int q = tid + (jb + j) * kTT;
-                        if (vs[j].w == tk && vt[j].w == tk) {
-                            const long long r = (long long)__ldg(P.cost + pos_arc(q)) + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
-                            const int st = pf_st[q];
-                            pf_rcb[q] = r; pf_key[q] = st > 0 ? r : (st < 0 ? -r : 0);
-                            pf_lab[q] = make_int2(vs[j].z, vt[j].z);
-                            pf_missing &= ~(1u << (jb + j));
+                        vs[j] = ld_mail(sbuf + 2 * q); vt[j] = ld_mail(sbuf + 2 * q + 1);
+                        cs[j] = __ldg(P.cost + (q < p2 ? cursor - d0 + q : q - p2));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
+                        const int q = tid + (jb + j) * kTT;
+                        if (vs[j].w == tkw && vt[j].w == tkw) {
+                            rcb[q] = (long long)cs[j] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            lab[q] = make_int2(vs[j].z, vt[j].z);
+                            missing &= ~(1u << (jb + j));
                         }
                     }
                 }
-                if (!block) return pf_missing == 0;
-                if (!__syncthreads_or(pf_missing != 0)) return true;
+                if (!__syncthreads_or(missing != 0)) return true;
                 if (spin_check(spins, t0, P)) sh.abort = 1;
                 if (__syncthreads_or(sh.abort)) return false;
             }
+        };
+        // one end of an arc through the pending updates: label x as of the basis of the records, `nrep` updates to replay.
+        // Returns the sum of the sigmas of the updates that moved the node (UpdatePotentials, NS.cs:1185-1209); x becomes the label now.
+        auto replay_end = [&](int& x, int nrep) -> long long {
+            long long add = 0;
+            if (nrep == 2 && U1.change) {
+                if ((unsigned)(x - U1.a) < (unsigned)U1.s) add += U1.sigma;
+                int nx, nd; relabel(U1, x, 0, nx, nd); x = nx;
+            }
+            if (nrep >= 1 && U2.change) {
+                if ((unsigned)(x - U2.a) < (unsigned)U2.s) add += U2.sigma;
+                int nx, nd; relabel(U2, x, 0, nx, nd); x = nx;
+            }
+            return add;
         };
 
         for (;;) {
             const long long k = iterations + 1;
             const int seq = (int)(unsigned)k;
             const int par = (int)(k & 1);
+            const int h = par;
             TICK(t_wdone);
             if (probe_thr) sh.bk.pr_mark = (unsigned long long)clock64();
             // ================================================================ FindEnteringArc (NS.cs:1339-1397), post ENTER(k)
-            // Round r prices block r of the scan, offsets [r * B, (r + 1) * B) from the cursor.  Round 0 is staged already: its node
-            // records were served BEFORE the previous pivot's update was applied (sg_upto == k - 2); that one update is replayed from its
-            // closed form, so pricing waits for nobody.  Later rounds (3-4 % of the pivots) are requested, staged and priced the same way.
-            int win_p = -1, search_end = 0;
+            // Round r prices block r of the scan, offsets [r * B, (r + 1) * B) from the cursor.  Round 0 is staged (see above); when it is
+            // not (mispredicted place, first pivots) and in later rounds (one pivot in ten) the block is requested, staged and collected here.
+            int win_p = -1, search_end = 0, nrep = 0;
             for (int r = 0;; ++r) {
                 const long long o_lo = (long long)r * B;
                 if (r > 0 && o_lo >= S) { search_end = S; break; }
                 const int cnt = (int)min((long long)B, (long long)S - o_lo);
                 int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
-                if (!(sg_cursor == cur && sg_cnt == cnt && sg_upto >= k - 2)) {
+                nrep = (int)(unsigned)(k - 1) - hb_basis[h];
+                if (!(r == 0 && hb_ok[h] && hb_cur[h] == cur && hb_cnt[h] == cnt && (unsigned)nrep <= 2u && sg_cursor == cur && sg_cnt == cnt)) {
                     ++ticket;
                     __syncthreads();                                        // the staging area is no longer read
+                    post_request(par, seq, cur, cnt, ticket, 2);
                     layout(cur, cnt);
-                    post_request(par, seq, cur, cnt, ticket);
-                    stage_begin(0); arm_collect(); stage_finish();
-                    if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                    sg_upto = k - 1;
-                    if (probe_thr && r > 0) sh.bk.rounds_total++;
+                    stage_begin(0); stage_finish();
+                    if (!collect(h, cur, cnt, ticket, 2)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    hb_cur[h] = cur; hb_cnt[h] = cnt; hb_basis[h] = (int)(unsigned)(k - 1); hb_ok[h] = true; nrep = 0;
+                    if (probe_thr) sh.bk.rounds_total++;
                 }
-                const bool replay = sg_upto < k - 1 && Uprev.change;
-                const unsigned ra = replay ? (unsigned)Uprev.a : 0u, rs = replay ? (unsigned)Uprev.s : 0u;   // rs == 0: nothing matches
+                // ---- the pricing loop: two positions per 128-bit shared-memory load
+                const long long* const rcb = pf_rcb + h * kStagePos;
+                const int2* const lab = pf_lab + h * kStagePos;
+                // interval tests of the updates to replay ([a, a+s): re-hung subtree, [lo, lo+len): labels that shift by `by`); s == 0: no-op
+                const bool r1 = nrep == 2 && U1.change, r2 = nrep >= 1 && U2.change;
+                const unsigned a1 = (unsigned)U1.a, s1 = r1 ? (unsigned)U1.s : 0u, a2 = (unsigned)U2.a, s2 = r2 ? (unsigned)U2.s : 0u;
+                const unsigned lo1 = (unsigned)(U1.b < U1.a ? U1.b + 1 : U1.a + U1.s), len1 = r1 ? (unsigned)(U1.b < U1.a ? U1.a - U1.b - 1 : U1.b - U1.a - U1.s + 1) : 0u;
+                const int by1 = U1.b < U1.a ? U1.s : -U1.s;
                 long long bk = 0;
                 int bp = -1;
-                for (int i = tid; i < (sg_pt >> 1); i += kTT) {              // two positions per 128-bit shared-memory load
-                    const longlong2 kk = reinterpret_cast<const longlong2*>(pf_key)[i];
-                    const int4 ll = reinterpret_cast<const int4*>(pf_lab)[i];
-                    long long v0 = kk.x, v1 = kk.y;
-                    // UpdatePotentials of the pending pivot (NS.cs:1185-1209): pi += sigma inside the re-hung interval (rare)
-                    if (((unsigned)ll.x - ra < rs) | ((unsigned)ll.y - ra < rs)) {
-                        long long v = pf_rcb[2 * i]; const int st = pf_st[2 * i];
-                        if ((unsigned)ll.x - ra < rs) v += Uprev.sigma;
-                        if ((unsigned)ll.y - ra < rs) v -= Uprev.sigma;
-                        v0 = st > 0 ? v : (st < 0 ? -v : 0);
+                for (int i = tid; i < (sg_pt >> 1); i += kTT) {
+                    const longlong2 vv = reinterpret_cast<const longlong2*>(rcb)[i];
+                    const int4 ll = reinterpret_cast<const int4*>(lab)[i];
+                    const int2 ss = reinterpret_cast<const int2*>(pf_st)[i];
+                    long long v0 = vv.x, v1 = vv.y;
+                    int xa = ll.x, xb = ll.y, xc = ll.z, xd = ll.w;
+                    // rare: an end was re-hung by the older update - its new label needs the stem (relabel)
+                    if (((unsigned)xa - a1 < s1) | ((unsigned)xb - a1 < s1) | ((unsigned)xc - a1 < s1) | ((unsigned)xd - a1 < s1)) [[unlikely]] {
+                        v0 = vv.x + replay_end(xa, nrep) - replay_end(xb, nrep);
+                        v1 = vv.y + replay_end(xc, nrep) - replay_end(xd, nrep);
+                    } else {
+                        if ((unsigned)xa - lo1 < len1) xa += by1;
+                        if ((unsigned)xb - lo1 < len1) xb += by1;
+                        if ((unsigned)xc - lo1 < len1) xc += by1;
+                        if ((unsigned)xd - lo1 < len1) xd += by1;
+                        if ((unsigned)xa - a2 < s2) v0 += U2.sigma;
+                        if ((unsigned)xb - a2 < s2) v0 -= U2.sigma;
+                        if ((unsigned)xc - a2 < s2) v1 += U2.sigma;
+                        if ((unsigned)xd - a2 < s2) v1 -= U2.sigma;
                     }
-                    if (((unsigned)ll.z - ra < rs) | ((unsigned)ll.w - ra < rs)) {
-                        long long v = pf_rcb[2 * i + 1]; const int st = pf_st[2 * i + 1];
-                        if ((unsigned)ll.z - ra < rs) v += Uprev.sigma;
-                        if ((unsigned)ll.w - ra < rs) v -= Uprev.sigma;
-                        v1 = st > 0 ? v : (st < 0 ? -v : 0);
-                    }
+                    v0 = ss.x > 0 ? v0 : (ss.x < 0 ? -v0 : 0);
+                    v1 = ss.y > 0 ? v1 : (ss.y < 0 ? -v1 : 0);
                     if (v0 < bk) { bk = v0; bp = 2 * i; }
                     if (v1 < bk) { bk = v1; bp = 2 * i + 1; }
                 }
@@ -606,10 +644,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // the winner's raw fields, read by every thread before the staging area is reused
             int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0;
             long long w_up = 0, w_rcb = 0;
-            const bool w_replay = sg_upto < k - 1 && Uprev.change;
             if (have_win) {
-                w_arc = pos_arc(win_p); w_src = pf_src[win_p]; w_tgt = pf_tgt[win_p]; w_st = pf_st[win_p]; w_up = pf_up[win_p]; w_rcb = pf_rcb[win_p];
-                const int2 lab = pf_lab[win_p]; w_ins = lab.x; w_int = lab.y;
+                w_arc = pos_arc(win_p); w_src = pf_src[win_p]; w_tgt = pf_tgt[win_p]; w_st = pf_st[win_p]; w_up = pf_up[win_p];
+                w_rcb = pf_rcb[h * kStagePos + win_p];
+                const int2 lab = pf_lab[h * kStagePos + win_p]; w_ins = lab.x; w_int = lab.y;
             }
             // NS.cs:1397-1438: cursor, counters, adaptive block size
             if (probe_thr) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
@@ -629,18 +667,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (search_end < S || S % Bold == 0) { int e = next_arc + search_end - 1; if (e >= S) e -= S; next_arc = e; }
             }
             const int nb0 = B < S ? B : S;
+            // the block of pivot k+2 at its predicted place: where the cursor ends up if the next search stops in its first block
+            int c2 = next_arc;
+            if (nb0 < S || S % B == 0) { c2 = next_arc + nb0 - 1; if (c2 >= S) c2 -= S; }
             if (have_win) ++ticket;
             __syncthreads();                                                // every thread has read the winner: the staging area is free
             if (warp == 0) {
-                // ---- warp 0 (all lanes the same values): replay the pending update on the winner, post ENTER(k) + the request for
-                // the next pivot's block, which is exactly known now
-                if (have_win && w_replay) {
-                    if ((unsigned)(w_ins - Uprev.a) < (unsigned)Uprev.s) w_rcb += Uprev.sigma;
-                    if ((unsigned)(w_int - Uprev.a) < (unsigned)Uprev.s) w_rcb -= Uprev.sigma;
-                    int nx, nd;
-                    relabel(Uprev, w_ins, 0, nx, nd); w_ins = nx;
-                    relabel(Uprev, w_int, 0, nx, nd); w_int = nx;
-                }
+                // ---- warp 0 (all lanes the same values): replay the pending updates on the winner, post ENTER(k) + the staging request
+                if (have_win) { w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep); }
                 if (lane < 5 * kRepEnt) {
                     const int wd = lane % 5;
                     int4 o;
@@ -649,7 +683,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     else if (wd == 1) o = make_int4(w_st, w_ins, w_int, seq);
                     else if (wd == 2) o = make_int4(lo32(w_rcb), hi32(w_rcb), 0, seq);
                     else if (wd == 3) o = make_int4(lo32(w_up), hi32(w_up), 0, seq);
-                    else o = make_int4(next_arc, nb0, ticket, seq);
+                    else o = make_int4(c2, nb0, ticket * 4 + h, seq);
                     if (have_win || wd < 4) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 5) * kMailWords + wd, o);
                 }
                 if (lane == 0) { Ent e; e.arc = w_arc; e.src = w_src; e.tgt = w_tgt; e.state = w_st; e.in_s = w_ins; e.in_t = w_int; e.upper = w_up; e.rcb = w_rcb; sh.win = e; }
@@ -657,58 +691,53 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (!have_win) { status = ST_OPTIMAL; break; }
             iterations = k;
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
-            // ---- the other warps meanwhile: arc data of the next block streams from DRAM; the block after it is pulled into L2
+            // what hot copy h will hold: the block requested just now (served from the basis before update k)
+            const int req_tk = ticket;
+            hb_cur[h] = c2; hb_cnt[h] = nb0; hb_basis[h] = (int)(unsigned)(k - 1); hb_ok[h] = false;
+            // ---- the other warps meanwhile: cold part of the next pivot's block (exactly known); the one after it is pulled into L2
             layout(next_arc, nb0);
-            sg_upto = k - 1;
             if (warp > 0) {
                 stage_begin(32);
-                if (nb0 < S) {
-                    int c2 = next_arc + nb0 - 1; if (c2 >= S) c2 -= S;
-                    for (int q = (tid - 32) * 32; q < nb0; q += (kTT - 32) * 32) {
-                        int idx = c2 + q; if (idx >= S) idx -= S;
-                        prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
-                        prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
-                    }
+                for (int q = (tid - 32) * 32; q < nb0; q += (kTT - 32) * 32) {
+                    int idx = c2 + q; if (idx >= S) idx -= S;
+                    prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
+                    prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
                 }
             }
-            arm_collect();
             TICK(t_price);
             PROBE(1);
-            // while the owners scan: finish the arc data of the next block, collect its node records (served before the scan)
-            stage_finish();
+            // ---- while the owners scan: collect the node records of the next pivot's block (requested one pivot ago, served long ago)
+            // when they are for the right place; otherwise the next pricing requests them itself
+            {
+                const int h1 = h ^ 1;
+                if (hb_cur[h1] == next_arc && hb_cnt[h1] == nb0 && !hb_ok[h1] && k >= 2) {
+                    if (!collect(h1, next_arc, nb0, last_tk, h1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    hb_ok[h1] = true;
+                } else if (!hb_ok[h1] || hb_cur[h1] != next_arc || hb_cnt[h1] != nb0) hb_ok[h1] = false;
+            }
+            last_tk = req_tk;
             PROBE(2);
-            if (!collect_staged(ticket, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            stage_finish();
             const Ent E = sh.win;                                           // (complete: barriers in between)
             PROBE(3);
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<true>(seq, par, E, 0, D, U);
             if (rcd != 0) { status = rcd; break; }
             // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them - state[] in global memory and, when the arc
-            // lies in the block staged for the next pivot, its copy (and pricing key) in shared memory, staged before this decision
-            if (tid == 0) {
-                const int arc0 = E.arc, st0 = D.change ? STATE_TREE : -E.state;
-                const int arc1 = D.change ? D.out.pd >> 1 : -1, st1 = (D.out.zero & 1) ? STATE_LOWER : STATE_UPPER;
-                P.state[arc0] = st0;
-                sh.patch[0] = arc0; sh.patch[1] = st0; sh.patch[2] = arc1; sh.patch[3] = st1;
-                if (arc1 >= 0) P.state[arc1] = st1;
-            }
-            Uprev = U;                                                              // replayed by the next pricing (see above)
-            PROBE(5);
-            __syncthreads();
-            if (tid < 2) {                                                          // the two arcs whose state this pivot changed, if staged
-                const int arc = sh.patch[2 * tid], st = sh.patch[2 * tid + 1];
+            // lies in the block staged for the next pivot, its copy in shared memory, staged before this decision
+            if (tid < 2) {
+                const int arc = tid == 0 ? E.arc : (D.change ? D.out.pd >> 1 : -1);
+                const int st = tid == 0 ? (D.change ? STATE_TREE : -E.state) : ((D.out.zero & 1) ? STATE_LOWER : STATE_UPPER);
                 if (arc >= 0) {
+                    P.state[arc] = st;
                     int off = arc - sg_cursor; if (off < 0) off += S;
-                    if (off < sg_cnt) {
-                        const int p = off < sg_n1 ? sg_d0 + off : sg_p2 + off - sg_n1;
-                        const long long rr = pf_rcb[p];
-                        pf_st[p] = st; pf_key[p] = st > 0 ? rr : (st < 0 ? -rr : 0);
-                    }
+                    if (off < sg_cnt) pf_st[off < sg_n1 ? sg_d0 + off : sg_p2 + off - sg_n1] = st;
                 }
             }
+            U1 = U2; U2 = U; U2.longstem = 1;                                       // (this CTA stages no stems: relabel reads them in place)
             __syncthreads();
             TICK(t_update);
-            PROBE(7);
+            PROBE(5);
             if (P.stop_after > 0 && iterations >= P.stop_after) { status = ST_STOPPED_EARLY; break; }
         }
         if (tid == 0) sh.mode = B;                                                   // final block size, for the epilogue
@@ -718,6 +747,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // serve a staging request: for every end of arcs [cursor, cursor + cnt) that this CTA owns, write {pi, in, ticket} - the
         // node's record as of the basis this CTA holds right now - into the pricer's staging slots
         auto serve = [&](int cursor, int cnt, int tk) {
+            int4* const sbuf = P.stage + (size_t)(tk & 3) * 2 * kStagePos;
             // the range is one or (when it wraps at S) two linear pieces of the arc arrays; each is read as aligned 128-bit words
             // (the slots are the pricer's staging positions: piece 1 at d0 .., piece 2 at the next multiple of four)
             int seg_a = cursor, seg_n = min(cnt, S - cursor), pbase = cursor & 3, done_n = 0;
@@ -741,8 +771,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             for (int e = 0; e < 4; ++e) {
                                 if ((unsigned)(ob + e) < (unsigned)seg_n) {
                                     const unsigned js = (unsigned)(sv[e] - lo), jt = (unsigned)(tv[e] - lo);
-                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(P.stage + 2 * (pbase + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
-                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(P.stage + 2 * (pbase + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
+                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(sbuf + 2 * (pbase + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
+                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(sbuf + 2 * (pbase + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
                                 }
                             }
                         }
@@ -797,26 +827,6 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (E.arc < 0) { status = ST_OPTIMAL; break; }
             iterations = k;
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
-            // ---- first serve the staging request for the next pivot's block (it came with ENTER(k); the basis this CTA holds is the
-            // one before update k, which is what the pricer will replay update k on): the pricer collects the records while CYC(k) is
-            // in flight, so that its next pricing does not have to wait for them
-            if (!(nreq.w == seq && nreq.z != ticket)) {                  // word 5 had not arrived together with the others: fetch it
-                if (tid == 0) {
-                    int4 v = make_int4(0, 0, 0, 0);
-                    unsigned spins = 0; long long t0 = 0;
-                    for (;;) {
-                        v = ld_mail(line + 4);
-                        if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
-                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                    }
-                    sh.ent[4] = v;
-                }
-                __syncthreads();
-                nreq = sh.ent[4];
-            }
-            if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
-            PROBE(8);
-
             const bool lower_state = E.state == STATE_LOWER;
             const int first = lower_state ? E.src : E.tgt, second = lower_state ? E.tgt : E.src;      // NS.cs:948-957
             const int inF = lower_state ? E.in_s : E.in_t, inS = lower_state ? E.in_t : E.in_s;
@@ -915,6 +925,25 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
             }
             PROBE(11);
+            // ---- off the critical path: serve the staging request that came with ENTER(k) - the block of pivot k+2 at its predicted
+            // place.  The basis this CTA holds is the one before update k; the pricer replays updates k and k+1 on the records.
+            if (!(nreq.w == seq && nreq.z != ticket)) {                  // word 5 had not arrived together with the others: fetch it
+                if (tid == 0) {
+                    int4 v = make_int4(0, 0, 0, 0);
+                    unsigned spins = 0; long long t0 = 0;
+                    for (;;) {
+                        v = ld_mail(line + 4);
+                        if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
+                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                    }
+                    sh.ent[4] = v;
+                }
+                __syncthreads();
+                nreq = sh.ent[4];
+            }
+            if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
+            PROBE(8);
+
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<false>(seq, par, E, nc, D, U);
             if (rcd != 0) { status = rcd; break; }
@@ -1066,14 +1095,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
-constexpr size_t kPricerBytes = (size_t)(mcf::kStageMax + 16) * (4 * 8 + 3 * 4);   // up, rcb, key, lab + src, tgt, st
+constexpr size_t kPricerBytes = (size_t)(mcf::kStageMax + 16) * (8 + 2 * 16 + 3 * 4);   // up, 2 x (rcb, lab), src, tgt, st
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 
 extern "C" size_t mcfk_team_smem_bytes(int slice, int wide)
 {
     const size_t owner = (size_t)slice * (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
-    return kStemBytes + (owner > kPricerBytes ? owner : kPricerBytes) + 16;
+    return (kStemBytes + owner > kPricerBytes ? kStemBytes + owner : kPricerBytes) + 16;
 }
 
 // largest slice (nodes per owner CTA) that fits the opt-in shared memory of the device next to the kernel's static part
@@ -1084,7 +1113,7 @@ extern "C" int mcfk_team_max_slice(int device, int wide)
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, team_fn(wide)) != cudaSuccess) return -2;
     const long long avail = (long long)prop.sharedMemPerBlockOptin - (long long)fa.sharedSizeBytes - (long long)kStemBytes - 64;
-    if (avail < (long long)kPricerBytes) return -3;                             // the pricing CTA's staging area must fit too
+    if (avail + (long long)kStemBytes < (long long)kPricerBytes) return -3;     // the pricing CTA's staging area must fit too
     const long long s = avail / (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
     return (int)(s & ~7LL);
 }

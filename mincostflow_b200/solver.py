@@ -431,6 +431,12 @@ class NetworkSimplex:
             self._pots = out
         return self._pots
 
+    def state_after_stop(self):
+        """(flow[m], pi[n]) of the basis a bounded solve (stop_after_pivots) stopped at (mcf_get_state_after_stop)."""
+        f = np.zeros(self._m, np.int64); p = np.zeros(self._n, np.int64)
+        self._check(self._lib.mcf_get_state_after_stop(self._h, _ptr(f), _ptr(p)))
+        return f, p
+
     def device_results(self):
         """(flow pointer, potential pointer, device) of the result arrays in HBM (mcf_get_device_results)."""
         f = C.c_void_p(); p = C.c_void_p(); d = C.c_int32(-1)
