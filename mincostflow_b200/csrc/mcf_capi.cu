@@ -229,7 +229,7 @@ int bind_device(mcf_handle* h)
 void build_initial_basis(mcf_handle* h, int64_t art_cost)
 {
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n, root = n;
-    h->h_src.assign(S, 0); h->h_tgt.assign(S, 0); h->h_cost.assign(S, 0);
+    h->h_src.assign(S + 4, 0); h->h_tgt.assign(S + 4, 0); h->h_cost.assign(S + 4, 0);   // four zero entries behind the arrays: the team engine reads aligned 128-bit words
     h->h_state.assign(A, mcf::STATE_LOWER); h->h_flow.assign(A, 0); h->h_upper.assign(A, kInf);
     h->h_in.resize(n + 1); h->h_sz.resize(n + 1); h->h_parent.resize(n + 1); h->h_pd.resize(n + 1); h->h_pi.assign(n + 1, 0);
     for (int e = 0; e < m; ++e) {
@@ -358,8 +358,8 @@ int upload_team(mcf_handle* h, int team, int slice, int wide, mcf::TeamParams* P
     cudaStream_t st = h->stream;
     int64_t bytes = 0;
     auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };
-    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)S * 4));
-    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
+    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)(S + 4) * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)(S + 4) * 4));
+    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)(S + 4) * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
     CUDA_TRY(h, up(h->d_flow.p, h->h_flow.data(), (size_t)A * 8)); CUDA_TRY(h, up(h->d_upper.p, h->h_upper.data(), (size_t)A * 8));
     CUDA_TRY(h, up(h->d_in.p, h->h_in.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4));
     CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_dp.p, h->h_dp.data(), (size_t)(n + 1) * 4));

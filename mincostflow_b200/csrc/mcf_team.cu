@@ -463,8 +463,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         //   of 10), served by the owners off their critical path from the basis before update k, collected here one pivot later, and
         //   priced with updates k and k+1 replayed in closed form.  So in the steady state pricing waits for nobody.
         int sg_cursor = -1, sg_cnt = 0, sg_d0 = 0, sg_n1 = 0, sg_p2 = 0, sg_pt = 0;     // cold part: which block, its layout
-        int hb_cur[2] = {-1, -1}, hb_cnt[2] = {0, 0}, hb_basis[2] = {0, 0};             // hot copies: which block, as of which basis (low 32 bits of the pivot index)
-        bool hb_ok[2] = {false, false};                                                 // ... and whether its records are in shared memory
+        // hot copies 0 / 1: which block, as of which basis (low 32 bits of the pivot index), whether its records are in shared memory
+        int hb_cur0 = -1, hb_cur1 = -1, hb_cnt0 = 0, hb_cnt1 = 0, hb_basis0 = 0, hb_basis1 = 0;
+        bool hb_ok0 = false, hb_ok1 = false;
+        auto hb_set = [&](int h, int cur, int cnt, int basis, bool ok) {
+            if (h) { hb_cur1 = cur; hb_cnt1 = cnt; hb_basis1 = basis; hb_ok1 = ok; } else { hb_cur0 = cur; hb_cnt0 = cnt; hb_basis0 = basis; hb_ok0 = ok; }
+        };
         Pending U1, U2;                                  // the updates of pivots k-2 and k-1, replayed on the staged node records
         U1.valid = U1.change = U1.a = U1.s = U1.b = U1.longstem = U1.dshift = U1.par = U1.seq = 0; U1.ns = 1; U1.sigma = 0;
         U2 = U1;
@@ -484,18 +488,20 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int g = p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2;
                 cp_async16(pf_src + p, P.src + g); cp_async16(pf_tgt + p, P.tgt + g);
                 cp_async16(pf_up + p, P.upper + g); cp_async16(pf_up + p + 2, P.upper + g + 2);
+                cp_async16(pf_st + p, P.state + g);                      // (.cg: from L2, where this CTA's own state stores are)
             }
         };
         auto stage_finish = [&]() {
-            for (int c = tid; c < (sg_pt >> 2); c += kTT) {
-                const int p = 4 * c;
-                const int g = p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2;
-                int4 v = __ldcg(reinterpret_cast<const int4*>(P.state + g));
-                if (!pos_valid(p)) v.x = 0; if (!pos_valid(p + 1)) v.y = 0; if (!pos_valid(p + 2)) v.z = 0; if (!pos_valid(p + 3)) v.w = 0;
-                *reinterpret_cast<int4*>(pf_st + p) = v;
-            }
             cp_async_wait_all();
-            __syncthreads();                                            // states and arc data are visible to every thread
+            __syncthreads();                                            // arc data and states are visible to every thread
+            // positions of the aligned chunks that lie outside the block (at most three at each end of a piece) price as state 0
+            if (tid < 16) {
+                const int e = tid >> 2, i = tid & 3;                     // e: 0 before piece 1, 1 behind it, 2 behind piece 2 (3: unused)
+                const int p = e == 0 ? i : e == 1 ? sg_d0 + sg_n1 + i : sg_p2 + (sg_cnt - sg_n1) + i;
+                const int lim = e == 1 ? sg_p2 : sg_pt;
+                if (e < 3 && p < lim && !pos_valid(p)) pf_st[p] = 0;
+            }
+            __syncthreads();
         };
         // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage buffer `buf`" (word 4 of the ENTER line)
         auto post_request = [&](int par, int seq, int cursor, int cnt, int tk, int buf) {
@@ -503,45 +509,46 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         };
         // collect the served node records of block (cursor, cnt), request `tk` in stage buffer `buf`, into hot copy h: reduced-cost base and
         // labels per position.  Spins until complete; false = abandoned.
-        auto collect = [&](int h, int cursor, int cnt, int tk, int buf) -> bool {
+        auto collect = [&](int h, int cursor, int cnt, int tk, int buf, bool probes) -> bool {
             const int d0 = cursor & 3, n1 = min(cnt, S - cursor), p2 = (d0 + n1 + 3) & ~3;
             const int pt = cnt > n1 ? p2 + ((cnt - n1 + 3) & ~3) : p2;
             long long* const rcb = pf_rcb + h * kStagePos;
             int2* const lab = pf_lab + h * kStagePos;
             const int4* const sbuf = P.stage + (size_t)buf * 2 * kStagePos;
             const int tkw = tk * 4 + buf;
+            // the owners serve every position of the aligned chunks (the few that lie outside the block are real arcs too, or the
+            // zero padding behind the arrays; pricing masks them by state 0).  The arc costs come straight from the arc array (they
+            // may still be on their way from DRAM: all of them are requested before the first record is looked at).
             unsigned missing = 0;
+            int cs[kPos];
 #pragma unroll
             for (int j = 0; j < kPos; ++j) {
-                const int p = tid + j * kTT;
-                if (p < pt) {
-                    const bool valid = p < p2 ? (unsigned)(p - d0) < (unsigned)n1 : p - p2 < cnt - n1;
-                    if (valid) missing |= 1u << j;
-                    else { rcb[p] = 0; lab[p] = make_int2(0, 0); }      // label 0 (the root's) is never inside a re-hung interval
-                }
+                const int q = tid + j * kTT;
+                cs[j] = 0;
+                if (q < pt) { missing |= 1u << j; cs[j] = __ldcg(P.cost + (q < p2 ? cursor - d0 + q : q - p2)); }
             }
             unsigned spins = 0; long long t0 = 0;
             for (;;) {
 #pragma unroll
                 for (int jb = 0; jb < kPos; jb += 3) {                   // three record pairs in flight
                     int4 vs[3], vt[3];
-                    int cs[3];
 #pragma unroll
                     for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
                         const int q = tid + (jb + j) * kTT;
                         vs[j] = ld_mail(sbuf + 2 * q); vt[j] = ld_mail(sbuf + 2 * q + 1);
-                        cs[j] = __ldg(P.cost + (q < p2 ? cursor - d0 + q : q - p2));
                     }
 #pragma unroll
                     for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
                         const int q = tid + (jb + j) * kTT;
                         if (vs[j].w == tkw && vt[j].w == tkw) {
-                            rcb[q] = (long long)cs[j] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            rcb[q] = (long long)cs[jb + j] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
                             lab[q] = make_int2(vs[j].z, vt[j].z);
                             missing &= ~(1u << (jb + j));
                         }
                     }
+                    if (jb == 0 && probes) PROBE(7);
                 }
+                if (probes) PROBE(6);
                 if (!__syncthreads_or(missing != 0)) return true;
                 if (spin_check(spins, t0, P)) sh.abort = 1;
                 if (__syncthreads_or(sh.abort)) return false;
@@ -578,15 +585,16 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (r > 0 && o_lo >= S) { search_end = S; break; }
                 const int cnt = (int)min((long long)B, (long long)S - o_lo);
                 int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
-                nrep = (int)(unsigned)(k - 1) - hb_basis[h];
-                if (!(r == 0 && hb_ok[h] && hb_cur[h] == cur && hb_cnt[h] == cnt && (unsigned)nrep <= 2u && sg_cursor == cur && sg_cnt == cnt)) {
+                nrep = (int)(unsigned)(k - 1) - (h ? hb_basis1 : hb_basis0);
+                if (!(r == 0 && (h ? hb_ok1 : hb_ok0) && (h ? hb_cur1 : hb_cur0) == cur && (h ? hb_cnt1 : hb_cnt0) == cnt && (unsigned)nrep <= 2u && sg_cursor == cur && sg_cnt == cnt)) {
                     ++ticket;
                     __syncthreads();                                        // the staging area is no longer read
                     post_request(par, seq, cur, cnt, ticket, 2);
                     layout(cur, cnt);
-                    stage_begin(0); stage_finish();
-                    if (!collect(h, cur, cnt, ticket, 2)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                    hb_cur[h] = cur; hb_cnt[h] = cnt; hb_basis[h] = (int)(unsigned)(k - 1); hb_ok[h] = true; nrep = 0;
+                    stage_begin(0);
+                    if (!collect(h, cur, cnt, ticket, 2, false)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    stage_finish();
+                    hb_set(h, cur, cnt, (int)(unsigned)(k - 1), true); nrep = 0;
                     if (probe_thr) sh.bk.rounds_total++;
                 }
                 // ---- the pricing loop: two positions per 128-bit shared-memory load
@@ -619,8 +627,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         if ((unsigned)xc - a2 < s2) v1 += U2.sigma;
                         if ((unsigned)xd - a2 < s2) v1 -= U2.sigma;
                     }
-                    v0 = ss.x > 0 ? v0 : (ss.x < 0 ? -v0 : 0);
-                    v1 = ss.y > 0 ? v1 : (ss.y < 0 ? -v1 : 0);
+                    v0 *= (long long)ss.x;                                   // state is -1, 0 or +1 (SpanningTree.cs:53-71)
+                    v1 *= (long long)ss.y;
                     if (v0 < bk) { bk = v0; bp = 2 * i; }
                     if (v1 < bk) { bk = v1; bp = 2 * i + 1; }
                 }
@@ -635,12 +643,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);
                     if (ww >= 0) win_p = (int)sh.pk[ww].y;
                 }
+                PROBE(0);
                 if (win_p >= 0) { search_end = (int)min(o_lo + B, (long long)S); break; }
                 if (cnt >= S) { search_end = S; break; }
             }
             if (status == ST_ERR_BARRIER_TIMEOUT) break;
             const bool have_win = win_p >= 0;
-            PROBE(0);
             // the winner's raw fields, read by every thread before the staging area is reused
             int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0;
             long long w_up = 0, w_rcb = 0;
@@ -693,36 +701,39 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
             // what hot copy h will hold: the block requested just now (served from the basis before update k)
             const int req_tk = ticket;
-            hb_cur[h] = c2; hb_cnt[h] = nb0; hb_basis[h] = (int)(unsigned)(k - 1); hb_ok[h] = false;
-            // ---- the other warps meanwhile: cold part of the next pivot's block (exactly known); the one after it is pulled into L2
+            hb_set(h, c2, nb0, (int)(unsigned)(k - 1), false);
             layout(next_arc, nb0);
-            if (warp > 0) {
-                stage_begin(32);
-                for (int q = (tid - 32) * 32; q < nb0; q += (kTT - 32) * 32) {
-                    int idx = c2 + q; if (idx >= S) idx -= S;
-                    prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
-                    prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
-                }
-            }
             TICK(t_price);
             PROBE(1);
             // ---- while the owners scan: collect the node records of the next pivot's block (requested one pivot ago, served long ago)
             // when they are for the right place; otherwise the next pricing requests them itself
             {
                 const int h1 = h ^ 1;
-                if (hb_cur[h1] == next_arc && hb_cnt[h1] == nb0 && !hb_ok[h1] && k >= 2) {
-                    if (!collect(h1, next_arc, nb0, last_tk, h1)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                    hb_ok[h1] = true;
-                } else if (!hb_ok[h1] || hb_cur[h1] != next_arc || hb_cnt[h1] != nb0) hb_ok[h1] = false;
+                const int o_cur = h1 ? hb_cur1 : hb_cur0, o_cnt = h1 ? hb_cnt1 : hb_cnt0;
+                bool ok = false;
+                if (o_cur == next_arc && o_cnt == nb0 && k >= 2) {
+                    if (!collect(h1, next_arc, nb0, last_tk, h1, true)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    ok = true;
+                }
+                if (h1) hb_ok1 = ok; else hb_ok0 = ok;
             }
             last_tk = req_tk;
             PROBE(2);
-            stage_finish();
-            const Ent E = sh.win;                                           // (complete: barriers in between)
+            // ---- cold part of the next pivot's block (exactly known) streams in behind the records (loads complete in issue order
+            // on an SM: the records, L2 hits, must not queue behind DRAM misses); the block after it is pulled into L2
+            stage_begin(0);
+            for (int q = tid * 32; q < nb0; q += kTT * 32) {
+                int idx = c2 + q; if (idx >= S) idx -= S;
+                prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
+                prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
+            }
+            __syncthreads();
+            const Ent E = sh.win;
             PROBE(3);
             Dec D; Pending U;
             const int rcd = gather_decide.template operator()<true>(seq, par, E, 0, D, U);
             if (rcd != 0) { status = rcd; break; }
+            stage_finish();                                                         // (arrived while CYC(k) was in flight)
             // arc states (ChangeFlow, NS.cs:1031-1039): only the pricing scans read them - state[] in global memory and, when the arc
             // lies in the block staged for the next pivot, its copy in shared memory, staged before this decision
             if (tid < 2) {
@@ -769,11 +780,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const int ob = a0 + 4 * ch - seg_a;                 // offset of the chunk's first arc inside the piece
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                if ((unsigned)(ob + e) < (unsigned)seg_n) {
-                                    const unsigned js = (unsigned)(sv[e] - lo), jt = (unsigned)(tv[e] - lo);
-                                    if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(sbuf + 2 * (pbase + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
-                                    if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(sbuf + 2 * (pbase + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
-                                }
+                                // (every element of the aligned chunk, also the few outside the block: the pricer expects a record per position)
+                                const unsigned js = (unsigned)(sv[e] - lo), jt = (unsigned)(tv[e] - lo);
+                                if (js < (unsigned)cntn) { const long long p = __ldcg(P.pi + sv[e]); st_mail(sbuf + 2 * (pbase + ob + e), make_int4(lo32(p), hi32(p), in_s[js], tk)); }
+                                if (jt < (unsigned)cntn) { const long long p = __ldcg(P.pi + tv[e]); st_mail(sbuf + 2 * (pbase + ob + e) + 1, make_int4(lo32(p), hi32(p), in_s[jt], tk)); }
                             }
                         }
                     }
