@@ -311,7 +311,7 @@ int choose_grid(mcf_handle* h, int* sms_out)
 
 // Team engine (mcf_team.cu): CTA 0 prices, the others own node slices that stay in shared memory.
 // Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine).
-int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out)
+int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out, int* pricers_out)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->opt.device) != cudaSuccess) return 0;
@@ -324,21 +324,26 @@ int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out)
     if (limit < 2) return 0;
     const long long nodes = (long long)h->n + 1;
     const long long need = (nodes + max_slice - 1) / max_slice;                 // owners the slices need at least
-    if (need > limit - 1) return 0;
+    // pricers: the block is split over them (each stages, collects and prices its share); about 768 arcs each, at most 4
+    long long pricers = (max_block + 767) / 768;
+    if (pricers < 1) pricers = 1;
+    if (pricers > 4) pricers = 4;
+    if (pricers > limit - need) pricers = limit - need;
+    if (pricers < 1) return 0;
     // owners: ~1024 nodes each when SMs are to spare (fewer CTAs make every exchange cheaper), never fewer than needed
     long long owners = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (nodes + 1023) / 1024;
     if (owners < need) owners = need;
-    if (owners > limit - 1) owners = limit - 1;
+    if (owners > limit - pricers) owners = limit - pricers;
     long long slice = (nodes + owners - 1) / owners;
     slice = (slice + 7) & ~7LL;
     if (slice > max_slice) return 0;
-    const int team = (int)(owners + 1);
+    const int team = (int)(owners + pricers);
     if (mcfk_team_max_ctas(h->opt.device, (int)slice, wide) < team) return 0;
-    *slice_out = (int)slice;
+    *slice_out = (int)slice; *pricers_out = (int)pricers;
     return team;
 }
 
-int upload_team(mcf_handle* h, int team, int slice, int wide, mcf::TeamParams* P)
+int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::TeamParams* P)
 {
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
@@ -347,7 +352,7 @@ int upload_team(mcf_handle* h, int team, int slice, int wide, mcf::TeamParams* P
     CUDA_TRY(h, h->d_pi.ensure(n + 1)); CUDA_TRY(h, h->d_ctl.ensure(1));
     int rep_ent = 1, rep_cyc = 1;
     mcfk_team_replicas(&rep_ent, &rep_cyc);
-    const size_t w_ent = (size_t)2 * rep_ent * mcf::kMailWords;
+    const size_t w_ent = (size_t)2 * rep_ent * pricers * mcf::kMailWords;
     const size_t w_cyc = (size_t)2 * rep_cyc * 5 * ((team + 7) & ~7);           // word-major: [2][replica][word 0..4][team padded to 8]
     const size_t w_stage = (size_t)2 * mcf::kReqMax;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
@@ -373,12 +378,12 @@ int upload_team(mcf_handle* h, int team, int slice, int wide, mcf::TeamParams* P
     P->pi = h->d_pi.p; P->in0 = h->d_in.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->dp0 = h->d_dp.p;
     P->ent = h->d_mail.p; P->cyc = P->ent + w_ent; P->stage = P->cyc + w_cyc;
     P->stemseg = h->d_mail.p + seg_off;
-    P->ctl = h->d_ctl.p; P->team = team; P->slice = slice; P->wide = wide;
+    P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
     return MCF_OK;
 }
 
 
-int solve_team(mcf_handle* h, int team, int slice, int wide, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
+int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
                clk::time_point t_total, int32_t* status_out, bool* needs_wide)
 {
     const int n = h->n, m = h->m, S = m + n;
@@ -386,7 +391,7 @@ int solve_team(mcf_handle* h, int team, int slice, int wide, int block, int dyn_
     h->metrics.grid_ctas = team;
     const auto t_h2d = clk::now();
     mcf::TeamParams P;
-    int rc = upload_team(h, team, slice, wide, &P);
+    int rc = upload_team(h, team, pricers, slice, wide, &P);
     if (rc != MCF_OK) return rc;
     if (has_lower) {
         CUDA_TRY(h, h->d_lower.ensure(m));
@@ -433,7 +438,7 @@ int solve_team(mcf_handle* h, int team, int slice, int wide, int block, int dyn_
     M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
     M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
-    M.pricer_ctas = 1; M.wide_flows = wide;
+    M.pricer_ctas = pricers; M.wide_flows = wide;
     // phase accumulators are SM clock ticks (reading %globaltimer costs microseconds); scale by the kernel's own ns / tick
     const double ns_per_clk = ctl.clk_total > 0 ? (double)ctl.ns_total / (double)ctl.clk_total : 0.0;
     M.pivot_search_time_us = ctl.ns_price * ns_per_clk / 1000.0; M.cycle_time_us = ctl.ns_cycle * ns_per_clk / 1000.0;
@@ -647,11 +652,11 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
         }
         const int max_block = (cfg.flags & MCF_FLAG_ADAPTIVE_BLOCK_SIZE) ? std::max(block, cfg.max_block_size) : block;
         for (; wide < 2; ++wide) {
-            int slice = 0;
-            const int team = choose_team(h, wide, std::min(max_block, S), &slice);
+            int slice = 0, pricers = 0;
+            const int team = choose_team(h, wide, std::min(max_block, S), &slice, &pricers);
             if (team <= 0) break;
             bool needs_wide = false;
-            rc = solve_team(h, team, slice, wide, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
+            rc = solve_team(h, team, pricers, slice, wide, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
             if (rc != MCF_OK || !needs_wide) return rc;
         }
         if (h->opt.engine == 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but the instance does not fit (n = %d)", n);

@@ -103,7 +103,7 @@ struct Params {
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
 constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages in shared memory (longer ones are read in place)
-constexpr int kStageMax = 4096;         // arcs of one pricing block staged in the pricing CTA's shared memory (= largest block size)
+constexpr int kStageMax = 3584;         // arcs of one pricing block staged in the pricing CTAs' shared memory (= largest block size)
 constexpr int kReqMax = 16384;          // arcs per explicit staging request (later rounds of a search)
 
 // per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
@@ -118,12 +118,13 @@ struct TeamParams {
     const long long* orig_lower;                         // [m] or nullptr
     long long* pi;                                       // [n+1] potentials (NS.cs:48); every entry is read and written by its owner CTA only
     const int* in0; const int* sz0; const int* pd0; const int* dp0;   // [n+1] initial basis: depth-first index, subtree size, pred word, depth
-    int4* ent;                                           // [2][kRepEnt][kMailWords]        pricer -> all: entering arc of the pivot + staging requests
+    int4* ent;                                           // [2][kRepEnt][pricers][kMailWords] pricer -> all: its candidate of the round; pricer 0 also the staging requests
     int4* cyc;                                           // [2][kRepCyc][5][team padded to 8] owner -> all: leaving-arc candidates, word-major
     int4* stemseg;                                       // [2][n+1][2]                     stem entries, indexed by depth
     int4* stage;                                         // [2 * kReqMax]                   owner -> pricer: {pi, in} of the arc ends of a requested range
     Ctl* ctl;
-    int team;                                            // CTAs: CTA 0 prices, CTAs [1, team) own node slices
+    int team;                                            // CTAs: [0, pricers) price, [pricers, team) own node slices
+    int pricers;
     int slice;                                           // nodes per owner
     int wide;                                            // 1: tree-arc flows / capacities resident as int64, 0: int32
     int block_size, dyn_min_block, max_block_size, adaptive, consecutive;

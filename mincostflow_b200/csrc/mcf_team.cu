@@ -43,6 +43,7 @@ constexpr int kPos = (kStagePos + kTT - 1) / kTT;       // positions per pricer 
 constexpr int kRepEnt = 4;                              // replicas of the ENTER record: a reader polls replica (cta % kRepEnt)
 constexpr int kRepCyc = 4;                              // replicas of every CYC record
 constexpr int kRelUnroll = 4;                           // nodes per thread in flight in the relabel pass
+constexpr int kMaxPricers = 6;                          // pricing CTAs of a team (4 words each + the request word are polled by one warp)
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
 // mailbox words: one 128-bit relaxed.gpu access each (single-copy atomic, PTX ISA 8.3+), polled until the sequence number matches
@@ -153,7 +154,8 @@ struct TeamShared {
     longlong2 pk[kTW];              // per-warp pricing winners: {reduced cost, position}
     Ent win;                        // entering arc of this pivot (pricer)
     int patch[4];                   // pricer: the two arc-state changes of this pivot
-    int4 ent[5];                    // ENTER record as received (owners): words 0-3 the entering arc, word 4 the staging request
+    int4 ent[5];                    // the winning ENTER record (words 0-3) and the staging request (word 4) as received
+    int4 erec[kMaxPricers][4];      // every pricer's record of the round
     int ncand, abort, cnt, mode, dpF, dpS, ovf;
 };
 
@@ -228,11 +230,11 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     __shared__ TeamShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = P.team, cta = blockIdx.x, nown = G - 1;
+    const int G = P.team, NP = P.pricers, cta = blockIdx.x, nown = G - NP;
     const int Gp = (G + 7) & ~7;                         // CYC word arrays are padded to whole 128-byte lines
     const int n = P.n, S = P.S;
-    const bool pricer = cta == 0;
-    const int own = cta - 1;
+    const bool pricer = cta < NP;
+    const int own = cta - NP;
     const int lo = pricer ? 0 : own * P.slice;
     const int cntn = pricer ? 0 : max(0, min(n + 1, lo + P.slice) - lo);
 
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const pf_src = reinterpret_cast<int*>(pf_lab + 2 * kStagePos);
     int* const pf_tgt = pf_src + kStagePos;
     int* const pf_st = pf_tgt + kStagePos;
+    int* const pf_cost = pf_st + kStagePos;
 
     int status = ST_NOT_SOLVED;
     {
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     long long iterations = 0;
     // statistics and phase timers are kept by ONE thread of the last warp of CTA 0 (pricer: slots 0-7) and CTA 1 (first owner: 8-15):
     // it polls nothing and posts nothing, so that reading the clock never sits in front of a message
-    const bool probe_thr = tid == kTT - 32 && cta <= 1;
+    const bool probe_thr = tid == kTT - 32 && (cta == 0 || cta == NP);
     int cons_low = 0, cons_high = 0;                     // pricer: adaptive block size counters (NS.cs:1399-1438)
 #define PROBE(i) do { if (probe_thr && ((i) < 8) == (cta == 0)) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.pr[i] += t__ - sh.bk.pr_mark; sh.bk.pr_mark = t__; } } while (0)
 #define TICK(acc) do { if (probe_thr && cta == 0) { const unsigned long long t__ = (unsigned long long)clock64(); sh.bk.acc += t__ - sh.bk.t_mark; sh.bk.t_mark = t__; } } while (0)
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (tid < nown) {
                 // the records are stored word-major (word w of every owner side by side): consecutive lanes poll consecutive
                 // 16-byte words of the same lines.  Word 0 says whether the owner has candidates at all; only then are words 1-4 read.
-                const int4* const wbase = P.cyc + ((size_t)par * kRepCyc + cta % kRepCyc) * 5 * Gp + 1 + tid;
+                const int4* const wbase = P.cyc + ((size_t)par * kRepCyc + cta % kRepCyc) * 5 * Gp + NP + tid;
                 int4 w0;
                 if (!poll_word(wbase, seq, w0, P)) sh.abort = 1;
                 else {
@@ -463,6 +466,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         //   of 10), served by the owners off their critical path from the basis before update k, collected here one pivot later, and
         //   priced with updates k and k+1 replayed in closed form.  So in the steady state pricing waits for nobody.
         int sg_cursor = -1, sg_cnt = 0, sg_d0 = 0, sg_n1 = 0, sg_p2 = 0, sg_pt = 0;     // cold part: which block, its layout
+        int sg_plo = 0, sg_phi = 0;                      // ... and the positions this pricer stages and prices (whole 16-byte chunks)
         // hot copies 0 / 1: which block, as of which basis (low 32 bits of the pivot index), whether its records are in shared memory
         int hb_cur0 = -1, hb_cur1 = -1, hb_cnt0 = 0, hb_cnt1 = 0, hb_basis0 = 0, hb_basis1 = 0;
         bool hb_ok0 = false, hb_ok1 = false;
@@ -477,18 +481,21 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             sg_cursor = cursor; sg_cnt = cnt; sg_d0 = cursor & 3; sg_n1 = min(cnt, S - cursor);
             sg_p2 = (sg_d0 + sg_n1 + 3) & ~3;
             sg_pt = cnt > sg_n1 ? sg_p2 + ((cnt - sg_n1 + 3) & ~3) : sg_p2;
+            const int nch = sg_pt >> 2;
+            sg_plo = 4 * (int)((long long)cta * nch / NP); sg_phi = 4 * (int)((long long)(cta + 1) * nch / NP);
         };
         auto pos_valid = [&](int p) -> bool { return p < sg_p2 ? (unsigned)(p - sg_d0) < (unsigned)sg_n1 : p - sg_p2 < sg_cnt - sg_n1; };
         auto pos_arc = [&](int p) -> int { return p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2; };
         // cold part: src / tgt / capacity are immutable and go global -> shared with 16-byte cp.async; `state` is mutable (this
         // CTA is its only writer) and is read around L1 by stage_finish().  Threads [t0, kTT) take part in stage_begin.
         auto stage_begin = [&](int t0) {
-            for (int c = tid - t0; c < (sg_pt >> 2); c += kTT - t0) {
+            for (int c = (sg_plo >> 2) + tid - t0; c < (sg_phi >> 2); c += kTT - t0) {
                 const int p = 4 * c;
                 const int g = p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2;
                 cp_async16(pf_src + p, P.src + g); cp_async16(pf_tgt + p, P.tgt + g);
                 cp_async16(pf_up + p, P.upper + g); cp_async16(pf_up + p + 2, P.upper + g + 2);
                 cp_async16(pf_st + p, P.state + g);                      // (.cg: from L2, where this CTA's own state stores are)
+                cp_async16(pf_cost + p, P.cost + g);
             }
         };
         auto stage_finish = [&]() {
@@ -505,28 +512,24 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         };
         // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage buffer `buf`" (word 4 of the ENTER line)
         auto post_request = [&](int par, int seq, int cursor, int cnt, int tk, int buf) {
-            if (warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * kMailWords + 4, make_int4(cursor, cnt, tk * 4 + buf, seq));
+            if (cta == 0 && warp == 0 && lane < kRepEnt) st_mail(P.ent + ((size_t)par * kRepEnt + lane) * NP * kMailWords + 4, make_int4(cursor, cnt, tk * 4 + buf, seq));
         };
         // collect the served node records of block (cursor, cnt), request `tk` in stage buffer `buf`, into hot copy h: reduced-cost base and
         // labels per position.  Spins until complete; false = abandoned.
         auto collect = [&](int h, int cursor, int cnt, int tk, int buf, bool probes) -> bool {
             const int d0 = cursor & 3, n1 = min(cnt, S - cursor), p2 = (d0 + n1 + 3) & ~3;
             const int pt = cnt > n1 ? p2 + ((cnt - n1 + 3) & ~3) : p2;
+            const int nch = pt >> 2;
+            const int plo = 4 * (int)((long long)cta * nch / NP), phi = 4 * (int)((long long)(cta + 1) * nch / NP);
             long long* const rcb = pf_rcb + h * kStagePos;
             int2* const lab = pf_lab + h * kStagePos;
             const int4* const sbuf = P.stage + (size_t)buf * 2 * kStagePos;
             const int tkw = tk * 4 + buf;
             // the owners serve every position of the aligned chunks (the few that lie outside the block are real arcs too, or the
-            // zero padding behind the arrays; pricing masks them by state 0).  The arc costs come straight from the arc array (they
-            // may still be on their way from DRAM: all of them are requested before the first record is looked at).
+            // zero padding behind the arrays; pricing masks them by state 0)
             unsigned missing = 0;
-            int cs[kPos];
 #pragma unroll
-            for (int j = 0; j < kPos; ++j) {
-                const int q = tid + j * kTT;
-                cs[j] = 0;
-                if (q < pt) { missing |= 1u << j; cs[j] = __ldcg(P.cost + (q < p2 ? cursor - d0 + q : q - p2)); }
-            }
+            for (int j = 0; j < kPos; ++j) if (plo + tid + j * kTT < phi) missing |= 1u << j;
             unsigned spins = 0; long long t0 = 0;
             for (;;) {
 #pragma unroll
@@ -534,14 +537,14 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     int4 vs[3], vt[3];
 #pragma unroll
                     for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
-                        const int q = tid + (jb + j) * kTT;
+                        const int q = plo + tid + (jb + j) * kTT;
                         vs[j] = ld_mail(sbuf + 2 * q); vt[j] = ld_mail(sbuf + 2 * q + 1);
                     }
 #pragma unroll
                     for (int j = 0; j < 3; ++j) if (jb + j < kPos && (missing >> (jb + j) & 1u)) {
-                        const int q = tid + (jb + j) * kTT;
+                        const int q = plo + tid + (jb + j) * kTT;
                         if (vs[j].w == tkw && vt[j].w == tkw) {
-                            rcb[q] = (long long)cs[jb + j] + mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
+                            rcb[q] = mk64(vs[j].x, vs[j].y) - mk64(vt[j].x, vt[j].y);
                             lab[q] = make_int2(vs[j].z, vt[j].z);
                             missing &= ~(1u << (jb + j));
                         }
@@ -577,13 +580,16 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             TICK(t_wdone);
             if (probe_thr) sh.bk.pr_mark = (unsigned long long)clock64();
             // ================================================================ FindEnteringArc (NS.cs:1339-1397), post ENTER(k)
-            // Round r prices block r of the scan, offsets [r * B, (r + 1) * B) from the cursor.  Round 0 is staged (see above); when it is
-            // not (mispredicted place, first pivots) and in later rounds (one pivot in ten) the block is requested, staged and collected here.
-            int win_p = -1, search_end = 0, nrep = 0;
+            // Round r prices block r of the scan, offsets [r * B, (r + 1) * B) from the cursor; every pricer its share of the positions.
+            // Round 0 is staged (see above); when it is not (mispredicted place, first pivots) and in later rounds (one pivot in ten)
+            // the block is requested, staged and collected here.  After each round the pricers post their candidates; everybody
+            // (pricers and owners) reads all of them and picks the same winner: smallest reduced cost, then first in scan order.
+            int search_end = 0, nrep = 0;
+            bool have_win = false;
             for (int r = 0;; ++r) {
                 const long long o_lo = (long long)r * B;
-                if (r > 0 && o_lo >= S) { search_end = S; break; }
                 const int cnt = (int)min((long long)B, (long long)S - o_lo);
+                const bool last_round = o_lo + cnt >= S;
                 int cur = next_arc + (int)o_lo; if (cur >= S) cur -= S;
                 nrep = (int)(unsigned)(k - 1) - (h ? hb_basis1 : hb_basis0);
                 if (!(r == 0 && (h ? hb_ok1 : hb_ok0) && (h ? hb_cur1 : hb_cur0) == cur && (h ? hb_cnt1 : hb_cnt0) == cnt && (unsigned)nrep <= 2u && sg_cursor == cur && sg_cnt == cnt)) {
@@ -607,16 +613,17 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int by1 = U1.b < U1.a ? U1.s : -U1.s;
                 long long bk = 0;
                 int bp = -1;
-                for (int i = tid; i < (sg_pt >> 1); i += kTT) {
+                for (int i = (sg_plo >> 1) + tid; i < (sg_phi >> 1); i += kTT) {
                     const longlong2 vv = reinterpret_cast<const longlong2*>(rcb)[i];
                     const int4 ll = reinterpret_cast<const int4*>(lab)[i];
                     const int2 ss = reinterpret_cast<const int2*>(pf_st)[i];
-                    long long v0 = vv.x, v1 = vv.y;
+                    const int2 cc = reinterpret_cast<const int2*>(pf_cost)[i];
+                    long long v0 = vv.x + cc.x, v1 = vv.y + cc.y;            // cost + pi_s - pi_t
                     int xa = ll.x, xb = ll.y, xc = ll.z, xd = ll.w;
                     // rare: an end was re-hung by the older update - its new label needs the stem (relabel)
                     if (((unsigned)xa - a1 < s1) | ((unsigned)xb - a1 < s1) | ((unsigned)xc - a1 < s1) | ((unsigned)xd - a1 < s1)) [[unlikely]] {
-                        v0 = vv.x + replay_end(xa, nrep) - replay_end(xb, nrep);
-                        v1 = vv.y + replay_end(xc, nrep) - replay_end(xd, nrep);
+                        v0 += replay_end(xa, nrep) - replay_end(xb, nrep);
+                        v1 += replay_end(xc, nrep) - replay_end(xd, nrep);
                     } else {
                         if ((unsigned)xa - lo1 < len1) xa += by1;
                         if ((unsigned)xb - lo1 < len1) xb += by1;
@@ -638,25 +645,66 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (wl >= 0 && lane == wl) sh.pk[warp] = make_longlong2(bk, bp);
                 __syncthreads();
                 if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                {
-                    const longlong2 q = sh.pk[lane & (kTW - 1)];             // every warp: CTA arg-min of (rc, position) over the warp winners
+                if (warp == 0) {
+                    // ---- warp 0 (all lanes the same values): this pricer's candidate - arg-min of (rc, position) over the warp winners -
+                    // with the pending updates replayed on it, posted; then every pricer's record of this round is read
+                    const longlong2 q = sh.pk[lane & (kTW - 1)];
                     const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);
-                    if (ww >= 0) win_p = (int)sh.pk[ww].y;
+                    int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0, w_p = 0;
+                    long long w_up = 0, w_rcb = 0;
+                    if (ww >= 0) {
+                        w_p = (int)sh.pk[ww].y;
+                        w_arc = pos_arc(w_p); w_src = pf_src[w_p]; w_tgt = pf_tgt[w_p]; w_st = pf_st[w_p]; w_up = pf_up[w_p];
+                        w_rcb = pf_rcb[h * kStagePos + w_p] + pf_cost[w_p];
+                        const int2 lb = pf_lab[h * kStagePos + w_p]; w_ins = lb.x; w_int = lb.y;
+                        w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep);
+                    }
+                    if (lane < 4 * kRepEnt) {
+                        const int wd = lane & 3;
+                        int4 o;
+                        if (wd == 0) o = make_int4(w_arc, w_src, w_tgt, seq);
+                        else if (wd == 1) o = make_int4(w_st, w_ins, w_int, seq);
+                        else if (wd == 2) o = make_int4(lo32(w_rcb), hi32(w_rcb), w_p, seq);
+                        else o = make_int4(lo32(w_up), hi32(w_up), r * 2 + (last_round ? 1 : 0), seq);
+                        st_mail(P.ent + (((size_t)par * kRepEnt + (lane >> 2)) * NP + cta) * kMailWords + wd, o);
+                    }
+                    // all records of round r (a pricer that is already a round further has seen only "none" in this one)
+                    const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * NP * kMailWords;
+                    int4 v = make_int4(0, 0, 0, 0);
+                    unsigned spins = 0; long long t0 = 0;
+                    int best = -1;
+                    for (;;) {
+                        if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
+                        const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3) >> 1;    // the round of the record this lane's word belongs to
+                        const bool ok = lane >= 4 * NP || (v.w == seq && rd == r);
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        const bool ahead = lane < 4 * NP && v.w == seq && rd > r;
+                        if (__any_sync(0xffffffffu, ahead)) { v = make_int4(-1, 0, 0, seq); break; }   // somebody went on: this round found nothing
+                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                    }
+                    {
+                        const int arc = __shfl_sync(0xffffffffu, v.x, (lane & ~3));
+                        const int st = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 1);
+                        const int r_lo = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 2), r_hi = __shfl_sync(0xffffffffu, v.y, (lane & ~3) | 2);
+                        const int pp = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 2);
+                        best = warp_argmin(lane < 4 * NP && (lane & 3) == 0 && arc >= 0, (long long)st * mk64(r_lo, r_hi), pp);
+                    }
+                    if (best >= 0) {
+                        const int4 w0 = make_int4(__shfl_sync(0xffffffffu, v.x, best), __shfl_sync(0xffffffffu, v.y, best), __shfl_sync(0xffffffffu, v.z, best), 0);
+                        const int4 w1 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 1), __shfl_sync(0xffffffffu, v.y, best + 1), __shfl_sync(0xffffffffu, v.z, best + 1), 0);
+                        const int4 w2 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 2), __shfl_sync(0xffffffffu, v.y, best + 2), 0, 0);
+                        const int4 w3 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 3), __shfl_sync(0xffffffffu, v.y, best + 3), 0, 0);
+                        if (lane == 0) { Ent e; e.arc = w0.x; e.src = w0.y; e.tgt = w0.z; e.state = w1.x; e.in_s = w1.y; e.in_t = w1.z; e.rcb = mk64(w2.x, w2.y); e.upper = mk64(w3.x, w3.y); sh.win = e; }
+                    }
+                    if (lane == 0) sh.mode = best >= 0 ? 1 : 0;
                 }
+                __syncthreads();
+                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
                 PROBE(0);
-                if (win_p >= 0) { search_end = (int)min(o_lo + B, (long long)S); break; }
-                if (cnt >= S) { search_end = S; break; }
+                if (sh.mode) { have_win = true; search_end = (int)(o_lo + cnt); break; }
+                if (last_round) { search_end = S; break; }
             }
             if (status == ST_ERR_BARRIER_TIMEOUT) break;
-            const bool have_win = win_p >= 0;
-            // the winner's raw fields, read by every thread before the staging area is reused
-            int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0;
-            long long w_up = 0, w_rcb = 0;
-            if (have_win) {
-                w_arc = pos_arc(win_p); w_src = pf_src[win_p]; w_tgt = pf_tgt[win_p]; w_st = pf_st[win_p]; w_up = pf_up[win_p];
-                w_rcb = pf_rcb[h * kStagePos + win_p];
-                const int2 lab = pf_lab[h * kStagePos + win_p]; w_ins = lab.x; w_int = lab.y;
-            }
             // NS.cs:1397-1438: cursor, counters, adaptive block size
             if (probe_thr) { sh.bk.arcs_checked += search_end; sh.bk.rounds_total++; }
             if (have_win) {
@@ -678,24 +726,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // the block of pivot k+2 at its predicted place: where the cursor ends up if the next search stops in its first block
             int c2 = next_arc;
             if (nb0 < S || S % B == 0) { c2 = next_arc + nb0 - 1; if (c2 >= S) c2 -= S; }
-            if (have_win) ++ticket;
-            __syncthreads();                                                // every thread has read the winner: the staging area is free
-            if (warp == 0) {
-                // ---- warp 0 (all lanes the same values): replay the pending updates on the winner, post ENTER(k) + the staging request
-                if (have_win) { w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep); }
-                if (lane < 5 * kRepEnt) {
-                    const int wd = lane % 5;
-                    int4 o;
-                    if (!have_win) o = make_int4(-1, 0, 0, seq);
-                    else if (wd == 0) o = make_int4(w_arc, w_src, w_tgt, seq);
-                    else if (wd == 1) o = make_int4(w_st, w_ins, w_int, seq);
-                    else if (wd == 2) o = make_int4(lo32(w_rcb), hi32(w_rcb), 0, seq);
-                    else if (wd == 3) o = make_int4(lo32(w_up), hi32(w_up), 0, seq);
-                    else o = make_int4(c2, nb0, ticket * 4 + h, seq);
-                    if (have_win || wd < 4) st_mail(P.ent + ((size_t)par * kRepEnt + lane / 5) * kMailWords + wd, o);
-                }
-                if (lane == 0) { Ent e; e.arc = w_arc; e.src = w_src; e.tgt = w_tgt; e.state = w_st; e.in_s = w_ins; e.in_t = w_int; e.upper = w_up; e.rcb = w_rcb; sh.win = e; }
-            }
+            if (have_win) { ++ticket; post_request(par, seq, c2, nb0, ticket, h); }
             if (!have_win) { status = ST_OPTIMAL; break; }
             iterations = k;
             if (iterations > P.max_iterations) { status = ST_INFEASIBLE; break; }          // NS.cs:311-317
@@ -796,7 +827,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const long long k = iterations + 1;
             const int seq = (int)(unsigned)k;
             const int par = (int)(k & 1);
-            const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * kMailWords;
+            const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * NP * kMailWords;   // the pricers' records, this CTA's replica
             // ================================================================ wait for ENTER(k), serving staging requests meanwhile
             for (;;) {
                 if (warp == 0) {
@@ -804,14 +835,32 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     int4 v = make_int4(0, 0, 0, 0);
                     int mode = 0;
                     for (;;) {
-                        if (lane < 5) v = ld_mail(line + lane);
-                        const unsigned okm = __ballot_sync(0xffffffffu, lane < 5 && v.w == seq);
-                        if ((okm & 0xfu) == 0xfu) { mode = 1; break; }
-                        const int tk = __shfl_sync(0xffffffffu, v.z, 4);
-                        if ((okm & 0x10u) && tk != ticket) { mode = 2; break; }
+                        // lanes [0, 4 NP): word (lane & 3) of pricer (lane >> 2)'s record; lane 4 NP: the staging request (pricer 0's word 4)
+                        if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
+                        else if (lane == 4 * NP) v = ld_mail(line + 4);
+                        const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3);        // round * 2 + last-round flag of this lane's record
+                        const int rd0 = __shfl_sync(0xffffffffu, rd, 0);
+                        const bool ok = lane >= 4 * NP || (v.w == seq && rd == rd0);
+                        if (__all_sync(0xffffffffu, ok)) {
+                            // every record is of this pivot and of the same round: the one with the smallest reduced cost, then the first
+                            // in scan order, is the entering arc; none at all = the round found nothing (the last round: optimal)
+                            const int arc = __shfl_sync(0xffffffffu, v.x, (lane & ~3));
+                            const int st = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 1);
+                            const int r_lo = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 2), r_hi = __shfl_sync(0xffffffffu, v.y, (lane & ~3) | 2);
+                            const int pp = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 2);
+                            const int best = warp_argmin(lane < 4 * NP && (lane & 3) == 0 && arc >= 0, (long long)st * mk64(r_lo, r_hi), pp);
+                            if (best >= 0 || (rd0 & 1)) {
+                                const int b0 = best >= 0 ? best : 0;
+                                const int4 w = make_int4(__shfl_sync(0xffffffffu, v.x, b0 + (lane & 3)), __shfl_sync(0xffffffffu, v.y, b0 + (lane & 3)), __shfl_sync(0xffffffffu, v.z, b0 + (lane & 3)), seq);
+                                if (lane < 4) sh.ent[lane] = best >= 0 ? w : make_int4(-1, 0, 0, seq);
+                                mode = 1; break;
+                            }
+                        }
+                        const int4 rq = make_int4(__shfl_sync(0xffffffffu, v.x, 4 * NP), __shfl_sync(0xffffffffu, v.y, 4 * NP), __shfl_sync(0xffffffffu, v.z, 4 * NP), __shfl_sync(0xffffffffu, v.w, 4 * NP));
+                        if (rq.w == seq && rq.z != ticket) { if (lane == 0) sh.ent[4] = rq; mode = 2; break; }
                         if (spin_check(spins, t0, P)) { mode = 3; break; }
                     }
-                    if (lane < 5) sh.ent[lane] = v;
+                    if (mode == 1 && lane == 0) sh.ent[4] = make_int4(0, 0, 0, 0);             // (the request that comes with ENTER is fetched after the scan)
                     if (lane == 0) sh.mode = mode;
                 }
                 __syncthreads();
@@ -1105,7 +1154,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
-constexpr size_t kPricerBytes = (size_t)(mcf::kStageMax + 16) * (8 + 2 * 16 + 3 * 4);   // up, 2 x (rcb, lab), src, tgt, st
+constexpr size_t kPricerBytes = (size_t)(mcf::kStageMax + 16) * (8 + 2 * 16 + 4 * 4);   // up, 2 x (pi_s - pi_t, lab), src, tgt, st, cost
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 
