@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -325,13 +326,13 @@ int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out, int* pri
     const long long nodes = (long long)h->n + 1;
     const long long need = (nodes + max_slice - 1) / max_slice;                 // owners the slices need at least
     // pricers: the block is split over them (each stages, collects and prices its share); about 768 arcs each, at most 4
-    long long pricers = (max_block + 767) / 768;
+    // (mcf_options.lookahead_blocks > 0 sets their number, up to 6)
+    long long pricers = h->opt.lookahead_blocks > 0 ? std::min(h->opt.lookahead_blocks, 6) : std::min((max_block + 767) / 768, 4);
     if (pricers < 1) pricers = 1;
-    if (pricers > 4) pricers = 4;
     if (pricers > limit - need) pricers = limit - need;
     if (pricers < 1) return 0;
     // owners: ~1024 nodes each when SMs are to spare (fewer CTAs make every exchange cheaper), never fewer than needed
-    long long owners = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (nodes + 1023) / 1024;
+    long long owners = (nodes + 1023) / 1024;
     if (owners < need) owners = need;
     if (owners > limit - pricers) owners = limit - pricers;
     long long slice = (nodes + owners - 1) / owners;

@@ -155,7 +155,7 @@ struct TeamShared {
     Ent win;                        // entering arc of this pivot (pricer)
     int patch[4];                   // pricer: the two arc-state changes of this pivot
     int4 ent[5];                    // the winning ENTER record (words 0-3) and the staging request (word 4) as received
-    int4 erec[kMaxPricers][4];      // every pricer's record of the round
+    int4 crec[kTW][4];              // pricer: the candidate record every warp prepares
     int ncand, abort, cnt, mode, dpF, dpS, ovf;
 };
 
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             sg_p2 = (sg_d0 + sg_n1 + 3) & ~3;
             sg_pt = cnt > sg_n1 ? sg_p2 + ((cnt - sg_n1 + 3) & ~3) : sg_p2;
             const int nch = sg_pt >> 2;
-            sg_plo = 4 * (int)((long long)cta * nch / NP); sg_phi = 4 * (int)((long long)(cta + 1) * nch / NP);
+            sg_plo = 4 * (cta * nch / NP); sg_phi = 4 * ((cta + 1) * nch / NP);
         };
         auto pos_valid = [&](int p) -> bool { return p < sg_p2 ? (unsigned)(p - sg_d0) < (unsigned)sg_n1 : p - sg_p2 < sg_cnt - sg_n1; };
         auto pos_arc = [&](int p) -> int { return p < sg_p2 ? sg_cursor - sg_d0 + p : p - sg_p2; };
@@ -502,13 +502,13 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             cp_async_wait_all();
             __syncthreads();                                            // arc data and states are visible to every thread
             // positions of the aligned chunks that lie outside the block (at most three at each end of a piece) price as state 0
-            if (tid < 16) {
-                const int e = tid >> 2, i = tid & 3;                     // e: 0 before piece 1, 1 behind it, 2 behind piece 2 (3: unused)
+            // (the caller's next barrier orders these stores before the pricing loop)
+            if (tid >= 32 && tid < 48) {
+                const int e = (tid - 32) >> 2, i = tid & 3;              // e: 0 before piece 1, 1 behind it, 2 behind piece 2 (3: unused)
                 const int p = e == 0 ? i : e == 1 ? sg_d0 + sg_n1 + i : sg_p2 + (sg_cnt - sg_n1) + i;
                 const int lim = e == 1 ? sg_p2 : sg_pt;
                 if (e < 3 && p < lim && !pos_valid(p)) pf_st[p] = 0;
             }
-            __syncthreads();
         };
         // post a staging request "owners: write {pi, in} of both ends of arcs [cursor, cursor + cnt) into stage buffer `buf`" (word 4 of the ENTER line)
         auto post_request = [&](int par, int seq, int cursor, int cnt, int tk, int buf) {
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const int d0 = cursor & 3, n1 = min(cnt, S - cursor), p2 = (d0 + n1 + 3) & ~3;
             const int pt = cnt > n1 ? p2 + ((cnt - n1 + 3) & ~3) : p2;
             const int nch = pt >> 2;
-            const int plo = 4 * (int)((long long)cta * nch / NP), phi = 4 * (int)((long long)(cta + 1) * nch / NP);
+            const int plo = 4 * (cta * nch / NP), phi = 4 * ((cta + 1) * nch / NP);
             long long* const rcb = pf_rcb + h * kStagePos;
             int2* const lab = pf_lab + h * kStagePos;
             const int4* const sbuf = P.stage + (size_t)buf * 2 * kStagePos;
@@ -572,6 +572,35 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             return add;
         };
 
+        // warp 0: read every pricer's record of round r of this pivot; 1 = the round has a winner (written to sh.win), 0 = none
+        auto read_records = [&](int par, int seq, int r) -> int {
+            const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * NP * kMailWords;
+            int4 v = make_int4(0, 0, 0, 0);
+            unsigned spins = 0; long long t0 = 0;
+            for (;;) {
+                if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
+                const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3) >> 1;    // the round of the record this lane's word belongs to
+                const bool ok = lane >= 4 * NP || (v.w == seq && rd == r);
+                if (__all_sync(0xffffffffu, ok)) break;
+                // a pricer that is already a round further has seen only "none" in this one
+                const bool ahead = lane < 4 * NP && v.w == seq && rd > r;
+                if (__any_sync(0xffffffffu, ahead)) return 0;
+                if (spin_check(spins, t0, P)) { sh.abort = 1; return 0; }
+            }
+            const int arc = __shfl_sync(0xffffffffu, v.x, (lane & ~3));
+            const int st = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 1);
+            const int r_lo = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 2), r_hi = __shfl_sync(0xffffffffu, v.y, (lane & ~3) | 2);
+            const int pp = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 2);
+            const int best = warp_argmin(lane < 4 * NP && (lane & 3) == 0 && arc >= 0, (long long)st * mk64(r_lo, r_hi), pp);
+            if (best < 0) return 0;
+            const int4 w0 = make_int4(__shfl_sync(0xffffffffu, v.x, best), __shfl_sync(0xffffffffu, v.y, best), __shfl_sync(0xffffffffu, v.z, best), 0);
+            const int4 w1 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 1), __shfl_sync(0xffffffffu, v.y, best + 1), __shfl_sync(0xffffffffu, v.z, best + 1), 0);
+            const int4 w2 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 2), __shfl_sync(0xffffffffu, v.y, best + 2), 0, 0);
+            const int4 w3 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 3), __shfl_sync(0xffffffffu, v.y, best + 3), 0, 0);
+            if (lane == 0) { Ent e; e.arc = w0.x; e.src = w0.y; e.tgt = w0.z; e.state = w1.x; e.in_s = w1.y; e.in_t = w1.z; e.rcb = mk64(w2.x, w2.y); e.upper = mk64(w3.x, w3.y); sh.win = e; }
+            return 1;
+        };
+
         for (;;) {
             const long long k = iterations + 1;
             const int seq = (int)(unsigned)k;
@@ -584,8 +613,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // Round 0 is staged (see above); when it is not (mispredicted place, first pivots) and in later rounds (one pivot in ten)
             // the block is requested, staged and collected here.  After each round the pricers post their candidates; everybody
             // (pricers and owners) reads all of them and picks the same winner: smallest reduced cost, then first in scan order.
-            int search_end = 0, nrep = 0;
-            bool have_win = false;
+            int search_end = 0, nrep = 0, win_round = 0;
+            bool have_win = false, win_read = false;                  // win_read: sh.win holds the winner already
             for (int r = 0;; ++r) {
                 const long long o_lo = (long long)r * B;
                 const int cnt = (int)min((long long)B, (long long)S - o_lo);
@@ -600,6 +629,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     stage_begin(0);
                     if (!collect(h, cur, cnt, ticket, 2, false)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
                     stage_finish();
+                    __syncthreads();
                     hb_set(h, cur, cnt, (int)(unsigned)(k - 1), true); nrep = 0;
                     if (probe_thr) sh.bk.rounds_total++;
                 }
@@ -642,66 +672,51 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const int wl = warp_argmin(bp >= 0, bk, bp);                 // positions ascend with the scan offset: lowest position = first in scan order
                 if (lane == 0) sh.pk[warp] = make_longlong2(0, -1);
                 __syncwarp();
-                if (wl >= 0 && lane == wl) sh.pk[warp] = make_longlong2(bk, bp);
-                __syncthreads();
-                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
-                if (warp == 0) {
-                    // ---- warp 0 (all lanes the same values): this pricer's candidate - arg-min of (rc, position) over the warp winners -
-                    // with the pending updates replayed on it, posted; then every pricer's record of this round is read
-                    const longlong2 q = sh.pk[lane & (kTW - 1)];
-                    const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);
-                    int w_arc = -1, w_src = 0, w_tgt = 0, w_st = 0, w_ins = 0, w_int = 0, w_p = 0;
-                    long long w_up = 0, w_rcb = 0;
-                    if (ww >= 0) {
-                        w_p = (int)sh.pk[ww].y;
-                        w_arc = pos_arc(w_p); w_src = pf_src[w_p]; w_tgt = pf_tgt[w_p]; w_st = pf_st[w_p]; w_up = pf_up[w_p];
-                        w_rcb = pf_rcb[h * kStagePos + w_p] + pf_cost[w_p];
-                        const int2 lb = pf_lab[h * kStagePos + w_p]; w_ins = lb.x; w_int = lb.y;
-                        w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep);
-                    }
-                    if (lane < 4 * kRepEnt) {
-                        const int wd = lane & 3;
-                        int4 o;
-                        if (wd == 0) o = make_int4(w_arc, w_src, w_tgt, seq);
-                        else if (wd == 1) o = make_int4(w_st, w_ins, w_int, seq);
-                        else if (wd == 2) o = make_int4(lo32(w_rcb), hi32(w_rcb), w_p, seq);
-                        else o = make_int4(lo32(w_up), hi32(w_up), r * 2 + (last_round ? 1 : 0), seq);
-                        st_mail(P.ent + (((size_t)par * kRepEnt + (lane >> 2)) * NP + cta) * kMailWords + wd, o);
-                    }
-                    // all records of round r (a pricer that is already a round further has seen only "none" in this one)
-                    const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * NP * kMailWords;
-                    int4 v = make_int4(0, 0, 0, 0);
-                    unsigned spins = 0; long long t0 = 0;
-                    int best = -1;
-                    for (;;) {
-                        if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
-                        const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3) >> 1;    // the round of the record this lane's word belongs to
-                        const bool ok = lane >= 4 * NP || (v.w == seq && rd == r);
-                        if (__all_sync(0xffffffffu, ok)) break;
-                        const bool ahead = lane < 4 * NP && v.w == seq && rd > r;
-                        if (__any_sync(0xffffffffu, ahead)) { v = make_int4(-1, 0, 0, seq); break; }   // somebody went on: this round found nothing
-                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
-                    }
-                    {
-                        const int arc = __shfl_sync(0xffffffffu, v.x, (lane & ~3));
-                        const int st = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 1);
-                        const int r_lo = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 2), r_hi = __shfl_sync(0xffffffffu, v.y, (lane & ~3) | 2);
-                        const int pp = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 2);
-                        best = warp_argmin(lane < 4 * NP && (lane & 3) == 0 && arc >= 0, (long long)st * mk64(r_lo, r_hi), pp);
-                    }
-                    if (best >= 0) {
-                        const int4 w0 = make_int4(__shfl_sync(0xffffffffu, v.x, best), __shfl_sync(0xffffffffu, v.y, best), __shfl_sync(0xffffffffu, v.z, best), 0);
-                        const int4 w1 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 1), __shfl_sync(0xffffffffu, v.y, best + 1), __shfl_sync(0xffffffffu, v.z, best + 1), 0);
-                        const int4 w2 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 2), __shfl_sync(0xffffffffu, v.y, best + 2), 0, 0);
-                        const int4 w3 = make_int4(__shfl_sync(0xffffffffu, v.x, best + 3), __shfl_sync(0xffffffffu, v.y, best + 3), 0, 0);
-                        if (lane == 0) { Ent e; e.arc = w0.x; e.src = w0.y; e.tgt = w0.z; e.state = w1.x; e.in_s = w1.y; e.in_t = w1.z; e.rcb = mk64(w2.x, w2.y); e.upper = mk64(w3.x, w3.y); sh.win = e; }
-                    }
-                    if (lane == 0) sh.mode = best >= 0 ? 1 : 0;
+                if (wl >= 0 && lane == wl) {
+                    // every warp prepares the full record of its own candidate (the pending updates replayed on it), all warps side by
+                    // side: what is left to do after the barrier is one arg-min and the post
+                    const int w_p = bp;
+                    int w_ins, w_int;
+                    { const int2 lb = pf_lab[h * kStagePos + w_p]; w_ins = lb.x; w_int = lb.y; }
+                    long long w_rcb = pf_rcb[h * kStagePos + w_p] + pf_cost[w_p];
+                    w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep);
+                    const long long w_up = pf_up[w_p];
+                    sh.pk[warp] = make_longlong2(bk, bp);
+                    sh.crec[warp][0] = make_int4(pos_arc(w_p), pf_src[w_p], pf_tgt[w_p], seq);
+                    sh.crec[warp][1] = make_int4(pf_st[w_p], w_ins, w_int, seq);
+                    sh.crec[warp][2] = make_int4(lo32(w_rcb), hi32(w_rcb), w_p, seq);
+                    sh.crec[warp][3] = make_int4(lo32(w_up), hi32(w_up), r * 2 + (last_round ? 1 : 0), seq);
                 }
                 __syncthreads();
                 if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                // ---- warp 0: this pricer's candidate = arg-min of (rc, position) over the warp winners, posted at once
+                const longlong2 q = sh.pk[lane & (kTW - 1)];
+                const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);      // (every warp computes it: `mine` is needed by all)
+                const bool mine = ww >= 0;
+                if (warp == 0 && lane < 4 * kRepEnt) {
+                    const int wd = lane & 3;
+                    int4 o = mine ? sh.crec[ww][wd] : (wd == 3 ? make_int4(0, 0, r * 2 + (last_round ? 1 : 0), seq) : make_int4(-1, 0, 0, seq));
+                    st_mail(P.ent + (((size_t)par * kRepEnt + (lane >> 2)) * NP + cta) * kMailWords + wd, o);
+                }
                 PROBE(0);
-                if (sh.mode) { have_win = true; search_end = (int)(o_lo + cnt); break; }
+                win_round = r;
+                if (mine) {                                                                // this round has a winner (which one is read later)
+                    have_win = true; search_end = (int)(o_lo + cnt);
+                    if (NP == 1) {
+                        if (tid == 0) { const int4 c0 = sh.crec[ww][0], c1 = sh.crec[ww][1], c2r = sh.crec[ww][2], c3r = sh.crec[ww][3];
+                            Ent e; e.arc = c0.x; e.src = c0.y; e.tgt = c0.z; e.state = c1.x; e.in_s = c1.y; e.in_t = c1.z; e.rcb = mk64(c2r.x, c2r.y); e.upper = mk64(c3r.x, c3r.y); sh.win = e; }
+                        win_read = true;
+                    }
+                    break;
+                }
+                // no candidate here: did another pricer find one?
+                if (warp == 0) {
+                    const int outcome = read_records(par, seq, r);
+                    if (lane == 0) sh.mode = outcome;
+                }
+                __syncthreads();
+                if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                if (sh.mode) { have_win = true; win_read = true; search_end = (int)(o_lo + cnt); break; }
                 if (last_round) { search_end = S; break; }
             }
             if (status == ST_ERR_BARRIER_TIMEOUT) break;
@@ -753,12 +768,16 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // ---- cold part of the next pivot's block (exactly known) streams in behind the records (loads complete in issue order
             // on an SM: the records, L2 hits, must not queue behind DRAM misses); the block after it is pulled into L2
             stage_begin(0);
-            for (int q = tid * 32; q < nb0; q += kTT * 32) {
-                int idx = c2 + q; if (idx >= S) idx -= S;
+            int c3 = c2;                                                    // the block after the one requested just now
+            if (nb0 < S) { c3 = c2 + nb0 - 1; if (c3 >= S) c3 -= S; }
+            for (int q = (sg_plo + tid * 32); q < sg_phi; q += kTT * 32) {
+                int idx = c3 + q; if (idx >= S) idx -= S;
                 prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
                 prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
             }
+            if (!win_read && warp == 0) read_records(par, seq, win_round);  // (the other pricers' candidates have long arrived)
             __syncthreads();
+            if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
             const Ent E = sh.win;
             PROBE(3);
             Dec D; Pending U;
@@ -986,13 +1005,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             PROBE(11);
             // ---- off the critical path: serve the staging request that came with ENTER(k) - the block of pivot k+2 at its predicted
             // place.  The basis this CTA holds is the one before update k; the pricer replays updates k and k+1 on the records.
-            if (!(nreq.w == seq && nreq.z != ticket)) {                  // word 5 had not arrived together with the others: fetch it
+            // (stage buffer 2 = an explicit request of this pivot's search, which may still sit in the word; 0 / 1 = the one meant here.
+            // Pricer 0 may post it before the other pricers' candidates are out: then it was served inside the wait loop above.)
+            {
                 if (tid == 0) {
                     int4 v = make_int4(0, 0, 0, 0);
                     unsigned spins = 0; long long t0 = 0;
                     for (;;) {
                         v = ld_mail(line + 4);
-                        if (v.w == seq && v.z != ticket) break;          // (an explicit request of this pivot's search may still sit in the word)
+                        if (v.w == seq && (v.z & 3) != 2) break;
                         if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
                     }
                     sh.ent[4] = v;
@@ -1000,7 +1021,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 __syncthreads();
                 nreq = sh.ent[4];
             }
-            if (!sh.abort) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
+            if (!sh.abort && nreq.z != ticket) { serve(nreq.x, nreq.y, nreq.z); ticket = nreq.z; }
             PROBE(8);
 
             Dec D; Pending U;
