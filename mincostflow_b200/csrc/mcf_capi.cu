@@ -84,6 +84,7 @@ struct mcf_handle {
     DevBuf<long long> d_flow, d_upper, d_lower, d_pi, d_rc;
     DevBuf<mcf::PriceRec> d_part;
     DevBuf<mcf::CycEnt> d_list;
+    DevBuf<int> d_scratch;                                            // flat engine: stem scratch (mcf_device.cuh)
     DevBuf<mcf::Ctl> d_ctl;
     DevBuf<unsigned char> d_flush;
     DevBuf<long long> d_val;                                          // validator scratch
@@ -217,7 +218,7 @@ int bind_device(mcf_handle* h)
         if (h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; }
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
-        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
         h->d_mail.release(); h->d_dp.release(); h->d_val.release(); h->d_pi_final = nullptr;
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->device_bound = dev;
@@ -265,7 +266,7 @@ int upload_basis(mcf_handle* h, bool need_cache, int grid)
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
     CUDA_TRY(h, h->d_in.ensure(n + 1)); CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_parent.ensure(n + 1));
     CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_pi.ensure(n + 1));
-    CUDA_TRY(h, h->d_part.ensure((size_t)2 * grid)); CUDA_TRY(h, h->d_list.ensure((size_t)n + 1)); CUDA_TRY(h, h->d_ctl.ensure(1));
+    CUDA_TRY(h, h->d_part.ensure((size_t)2 * grid)); CUDA_TRY(h, h->d_list.ensure((size_t)n + 1)); CUDA_TRY(h, h->d_scratch.ensure((size_t)6 * (n + 1))); CUDA_TRY(h, h->d_ctl.ensure(1));
     if (need_cache) { CUDA_TRY(h, h->d_rc.ensure(S)); CUDA_TRY(h, cudaMemsetAsync(h->d_rc.p, 0, (size_t)S * 8, h->stream)); }
     cudaStream_t st = h->stream;
     int64_t bytes = 0;
@@ -288,7 +289,7 @@ void fill_params(mcf_handle* h, mcf::Params* P)
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p;
     P->flow = h->d_flow.p; P->upper = h->d_upper.p; P->orig_lower = nullptr; P->rc_cache = nullptr;
     P->in = h->d_in.p; P->sz = h->d_sz.p; P->parent = h->d_parent.p; P->pd = h->d_pd.p; P->pi = h->d_pi.p;
-    P->part = h->d_part.p; P->list = h->d_list.p; P->list_cap = h->n + 1; P->ctl = h->d_ctl.p;
+    P->part = h->d_part.p; P->list = h->d_list.p; P->list_cap = h->n + 1; P->stem_scratch = h->d_scratch.p; P->ctl = h->d_ctl.p;
 }
 
 int choose_grid(mcf_handle* h, int* sms_out)
@@ -524,7 +525,7 @@ void mcf_destroy(mcf_handle* h)
         cudaSetDevice(h->device_bound);
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
-        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_ctl.release(); h->d_flush.release();
+        h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
         h->d_mail.release(); h->d_dp.release(); h->d_val.release(); h->d_pi_final = nullptr;
         if (h->stream) cudaStreamDestroy(h->stream);
     }

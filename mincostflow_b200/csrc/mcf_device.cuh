@@ -17,8 +17,8 @@ namespace mcf {
 
 constexpr int kThreads = 1024;          // threads per CTA of the persistent pivot kernel
 constexpr int kWarps = kThreads / 32;
-constexpr int kListSmem = 3584;         // cycle entries staged in shared memory (32 B each = 112 KB)
-constexpr int kStemCap = 2048;          // longest stem (u_in .. u_out) handled by the in-kernel sort
+constexpr int kListSmem = 3584;         // cycle entries staged in shared memory (32 B each = 112 KB); longer cycles are read from global memory
+constexpr int kStemCap = 2048;          // longest stem (u_in .. u_out) ranked in shared memory; longer ones go through global scratch
 
 // SpanningTree.cs:53-71
 constexpr int STATE_UPPER = -1, STATE_TREE = 0, STATE_LOWER = 1;
@@ -85,6 +85,7 @@ struct Params {
     // work areas
     PriceRec* part;                     // [2][gridDim.x]
     CycEnt* list; int list_cap;
+    int* stem_scratch;                  // [6][n+1] flat engine: stems longer than kStemCap are ranked and read here
     Ctl* ctl;
     // pricing configuration (BlockSearchPivot ctor, NS.cs:1304-1337; adaptive rule :1399-1438)
     int kind;

@@ -534,8 +534,21 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
 
         // =============================================================== phase C: leaving arc + updates
         const int cnt = __ldcg(&P.ctl->list_count[par]);
-        if (cnt > kListSmem || cnt > P.list_cap) { status = ST_ERR_CYCLE_TOO_LONG; break; }
-        for (int t = tid; t < cnt; t += kThreads) {
+        if (cnt > P.list_cap) { status = ST_ERR_CYCLE_TOO_LONG; break; }            // (cannot happen: the list holds every node)
+        // a cycle of up to kListSmem nodes is staged in shared memory; a longer one (deep trees: paths, grids, road networks) is
+        // read in place from the global list - slower, never refused
+        const bool small = cnt <= kListSmem;
+        auto ent = [&](int t) -> CycEnt {
+            if (small) return s_list[t];
+            const int4* q = reinterpret_cast<const int4*>(P.list + t);
+            const int4 a = __ldcg(q), b = __ldcg(q + 1);
+            CycEnt c; c.u = a.x; c.in = a.y; c.sz = a.z; c.pd = a.w;
+            c.flow = (long long)(((unsigned long long)(unsigned)b.y << 32) | (unsigned)b.x);
+            c.d = (long long)(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z);
+            return c;
+        };
+        auto ent_in = [&](int t) -> int { return small ? s_list[t].in : __ldcg(&P.list[t].in); };
+        if (small) for (int t = tid; t < cnt; t += kThreads) {
             const int4* q = reinterpret_cast<const int4*>(P.list + t);
             int4* d = reinterpret_cast<int4*>(s_list + t);
             d[0] = __ldcg(q); d[1] = __ldcg(q + 1);
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
         __syncthreads();
         Key k1 = key_none(), k2 = key_none();
         for (int t = tid; t < cnt; t += kThreads) {
-            const CycEnt& ce = s_list[t];
+            const CycEnt ce = ent(t);
             const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
             Key k; k.a = ce.d; k.idx = t;
             if (side1) { k.b = -ce.in; if (key_less(k, k1)) k1 = k; }      // strict '<' from `first` upward: deepest minimum
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
             if (delta > 0) {
                 if (tid == 0) P.flow[in_arc] = sh.h_fl + val;
                 for (int t = tid; t < cnt; t += kThreads) {
-                    const CycEnt& ce = s_list[t];
+                    const CycEnt ce = ent(t);
                     const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
                     const bool on_src_side = side1 == (bool)src_side1;
                     const long long dv = (ce.pd & 1) ? val : -val;          // pred_dir * val
@@ -580,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
             if (tid == 0) {
                 if (change) {
                     P.state[in_arc] = STATE_TREE;
-                    const CycEnt& ce = s_list[out_idx];
+                    const CycEnt ce = ent(out_idx);
                     const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
                     const bool on_src_side = side1 == (bool)src_side1;
                     const long long dv = (ce.pd & 1) ? val : -val;
@@ -594,29 +607,51 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
 
         if (change) {
             // ---- stem = cycle nodes on u_in's side from u_in up to u_out, deepest first
-            const CycEnt out = s_list[out_idx];
+            const CycEnt out = ent(out_idx);
             const int a = out.in, s = out.sz;                               // old interval of the re-hung subtree
             const bool in_side1 = result == 1;
+            // scratch in global memory for stems longer than kStemCap (CTA 0 ranks them there, everybody reads them in place)
+            int* const g_tmp = P.stem_scratch, * const g_raw = g_tmp + (n + 1), * const g_u = g_raw + (n + 1), * const g_in = g_u + (n + 1),
+               * const g_z = g_in + (n + 1), * const g_pd = g_z + (n + 1);
             if (tid == 0) sh.nstem = 0;
             __syncthreads();
             for (int t = tid; t < cnt; t += kThreads) {
-                const CycEnt& ce = s_list[t];
+                const CycEnt ce = ent(t);
                 const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
                 if (side1 == in_side1 && ce.in >= a) {
                     const int p = atomicAdd(&sh.nstem, 1);
                     if (p < kStemCap) sh.tmp_idx[p] = t;
+                    if (cta == 0) g_tmp[p] = t;
                 }
             }
             __syncthreads();
             const int ns = sh.nstem;
-            if (ns > kStemCap) { status = ST_ERR_STEM_TOO_LONG; break; }
-            for (int p = tid; p < ns; p += kThreads) {                      // rank by counting (in[] values are distinct)
-                const CycEnt& ce = s_list[sh.tmp_idx[p]];
-                int rank = 0;
-                for (int q = 0; q < ns; ++q) rank += s_list[sh.tmp_idx[q]].in > ce.in;
-                sh.st_u[rank] = ce.u; sh.st_in[rank] = ce.in; sh.st_z[rank] = ce.sz; sh.st_pd[rank] = ce.pd;
+            const bool bigstem = ns > kStemCap;
+            if (!bigstem) {
+                for (int p = tid; p < ns; p += kThreads) {                  // rank by counting (in[] values are distinct)
+                    const CycEnt ce = ent(sh.tmp_idx[p]);
+                    int rank = 0;
+                    for (int q = 0; q < ns; ++q) rank += ent_in(sh.tmp_idx[q]) > ce.in;
+                    sh.st_u[rank] = ce.u; sh.st_in[rank] = ce.in; sh.st_z[rank] = ce.sz; sh.st_pd[rank] = ce.pd;
+                }
+                __syncthreads();
+            } else {
+                if (cta == 0) {
+                    for (int p = tid; p < ns; p += kThreads) g_raw[p] = ent_in(__ldcg(g_tmp + p));
+                    __syncthreads();
+                    for (int p = tid; p < ns; p += kThreads) {
+                        const CycEnt ce = ent(__ldcg(g_tmp + p));
+                        int rank = 0;
+                        for (int q = 0; q < ns; ++q) rank += __ldcg(g_raw + q) > ce.in;
+                        g_u[rank] = ce.u; g_in[rank] = ce.in; g_z[rank] = ce.sz; g_pd[rank] = ce.pd;
+                    }
+                }
+                if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }     // (every CTA sees the same list: same branch)
             }
-            __syncthreads();
+            auto stem_u = [&](int k) -> int { return bigstem ? __ldcg(g_u + k) : sh.st_u[k]; };
+            auto stem_in = [&](int k) -> int { return bigstem ? __ldcg(g_in + k) : sh.st_in[k]; };
+            auto stem_z = [&](int k) -> int { return bigstem ? __ldcg(g_z + k) : sh.st_z[k]; };
+            auto stem_pd = [&](int k) -> int { return bigstem ? __ldcg(g_pd + k) : sh.st_pd[k]; };
             if (ns > max_stem) max_stem = ns;
             moved_nodes += s;
 
@@ -629,12 +664,12 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
             // ---- parent / pred / pred_dir / succ_num of the stem and succ_num along both paths (CTA 0)
             if (cta == 0) {
                 for (int k = tid; k < ns; k += kThreads) {
-                    const int u = sh.st_u[k];
+                    const int u = stem_u(k);
                     if (k == 0) { P.parent[u] = v_in; P.pd[u] = in_arc * 2 + dir_new_up; P.sz[u] = s; }
-                    else { P.parent[u] = sh.st_u[k - 1]; P.pd[u] = sh.st_pd[k - 1] ^ 1; P.sz[u] = s - sh.st_z[k - 1]; }
+                    else { P.parent[u] = stem_u(k - 1); P.pd[u] = stem_pd(k - 1) ^ 1; P.sz[u] = s - stem_z(k - 1); }
                 }
                 for (int t = tid; t < cnt; t += kThreads) {
-                    const CycEnt& ce = s_list[t];
+                    const CycEnt ce = ent(t);
                     const bool side1 = (unsigned)(inF - ce.in) < (unsigned)ce.sz;
                     if (side1 != in_side1) P.sz[ce.u] = ce.sz + s;          // v_in .. join (NS.cs:1174-1177)
                     else if (ce.in < a) P.sz[ce.u] = ce.sz - s;             // v_out .. join (NS.cs:1179-1182)
@@ -648,14 +683,14 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
                     int lo = 0, hi = ns - 1;                                // smallest k with x in [st_in[k], st_in[k]+st_z[k])
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
-                        if ((unsigned)(x - sh.st_in[mid]) < (unsigned)sh.st_z[mid]) hi = mid; else lo = mid + 1;
+                        if ((unsigned)(x - stem_in(mid)) < (unsigned)stem_z(mid)) hi = mid; else lo = mid + 1;
                     }
                     int off;
-                    if (lo == 0) off = x - sh.st_in[0];
+                    if (lo == 0) off = x - stem_in(0);
                     else {
-                        int r = x - sh.st_in[lo];
-                        if (x > sh.st_in[lo - 1]) r -= sh.st_z[lo - 1];
-                        off = sh.st_z[lo - 1] + r;
+                        int r = x - stem_in(lo);
+                        if (x > stem_in(lo - 1)) r -= stem_z(lo - 1);
+                        off = stem_z(lo - 1) + r;
                     }
                     P.in[u] = base + off;
                     P.pi[u] = __ldcg(P.pi + u) + sigma;
