@@ -41,7 +41,7 @@ WORKLOADS = {
     "netgen18": (18, 1, 300_000),
     "netgen16": (16, 1, 0),               # config 2
     "netgen10k": ("10k", 1, 0),           # config 1 (NETGEN 10 000 nodes / 30 000 arcs)
-    "grid1024": ("grid", 1, 0),           # config 4 (1024 x 1024 time-expanded grid)
+    "grid1024": ("grid", 1, -400_000),    # config 4 (1024 x 1024 time-expanded grid); negative: a plain prefix (no checkpoints recorded)
     "batch18": (18, 8, 300_000),          # config 5: 64 instances of 2^18 nodes = 8 per GPU at 8 GPUs
 }
 MID_WINDOW = {20: 40_000, 18: 100_000}    # pivots timed from each mid-solve checkpoint (oracle/_ref/ckpt_*.npz)
@@ -72,11 +72,14 @@ def cpu_sample(p, k, prefix, scale=1.0):
     from oracle import oracle
     cfg = oracle.default_config()
     wins = []
-    prefix = int(prefix * scale)
+    prefix_only = prefix < 0
+    prefix = int(abs(prefix) * scale)
     r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=prefix)
     wins.append({"from_pivot": 0, "pivots": int(r.iterations), "seconds": r.loop_seconds})
     if prefix == 0:
         return r.iterations / r.loop_seconds, "the full solve", wins
+    if prefix_only:
+        return r.iterations / r.loop_seconds, f"the first {prefix} pivots of one solve only (flatters the CPU: its per-pivot cost grows over a solve)", wins
     ck = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", f"ckpt_{p.name}_*.npz")))
     rec = (recorded_cpu() or {}).get(p.name)
     if not ck or not rec:
@@ -405,7 +408,7 @@ def run_ours(args):
             out["cpu_baseline"]["sampling_error_vs_recorded_full_solve"] = cpu_v / full["oracle_port_pivots_per_s"] - 1.0
         if sample:
             ns = solvers[0]
-            ns.set_engine_options(stop_after_pivots=sample)
+            ns.set_engine_options(stop_after_pivots=abs(sample))
             ns._dirty = True
             t0 = time.perf_counter(); ns.Solve(); gw = time.perf_counter() - t0
             Ms = ns.GetMetrics()

@@ -453,7 +453,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     M.arcs_priced = ctl.arcs_checked; M.pricing_bytes = 16 * M.arcs_priced; M.engine = 2;
     h->total_cost = ctl.total_cost; h->d_pi_final = h->d_pi.p; h->supply_type_solved = h->opt.supply_type;
 
-    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots", (long long)ctl.iterations); }
+    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots (wait site %d of CTA %d)", (long long)ctl.iterations, ctl.pad0 / 1000, ctl.pad0 % 1000); }
     if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
         done(MCF_NOT_SOLVED);
         return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kTeamStemCap);

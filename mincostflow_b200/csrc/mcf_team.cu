@@ -160,7 +160,7 @@ struct TeamShared {
 };
 
 // time-out / abort check for spin loops; true = give up
-__device__ __forceinline__ bool spin_check(unsigned& spins, long long& t0, const TeamParams& P)
+__device__ __forceinline__ bool spin_check(unsigned& spins, long long& t0, const TeamParams& P, int site = 0)
 {
 #ifdef MCF_SPIN_SLEEP
     __nanosleep(MCF_SPIN_SLEEP);                        // back off: fewer polling requests in flight at L2
@@ -168,24 +168,27 @@ __device__ __forceinline__ bool spin_check(unsigned& spins, long long& t0, const
     if ((++spins & 255u) != 0) return false;
     if (t0 == 0) { t0 = clock64(); return false; }
     if (*(volatile int*)&P.ctl->abort) return true;
-    if ((unsigned long long)(clock64() - t0) > P.timeout_cycles) { *(volatile int*)&P.ctl->abort = 1; return true; }
+    if ((unsigned long long)(clock64() - t0) > P.timeout_cycles) {
+        if (atomicCAS(&P.ctl->abort, 0, 1) == 0) P.ctl->pad0 = site * 1000 + (int)blockIdx.x;      // who gave up first, and where (for the error message)
+        return true;
+    }
     return false;
 }
 
 // poll one self-validating word until its sequence number matches; false = abandoned (abort flag or time-out)
-__device__ __forceinline__ bool poll_word(const int4* p, int seq, int4& out, const TeamParams& P)
+__device__ __forceinline__ bool poll_word(const int4* p, int seq, int4& out, const TeamParams& P, int site = 1)
 {
     unsigned spins = 0; long long t0 = 0;
     for (;;) {
         const int4 v = ld_mail(p);
         if (v.w == seq) { out = v; return true; }
-        if (spin_check(spins, t0, P)) { out = v; return false; }
+        if (spin_check(spins, t0, P, site)) { out = v; return false; }
     }
 }
 
 // poll NW words of one record, all loads in flight together
 template <int NW>
-__device__ __forceinline__ bool poll_rec(const int4* rec, int seq, int4 (&w)[NW], const TeamParams& P)
+__device__ __forceinline__ bool poll_rec(const int4* rec, int seq, int4 (&w)[NW], const TeamParams& P, int site = 2)
 {
     unsigned spins = 0; long long t0 = 0;
     for (;;) {
@@ -195,7 +198,7 @@ __device__ __forceinline__ bool poll_rec(const int4* rec, int seq, int4 (&w)[NW]
 #pragma unroll
         for (int i = 0; i < NW; ++i) ok = ok && w[i].w == seq;
         if (ok) return true;
-        if (spin_check(spins, t0, P)) return false;
+        if (spin_check(spins, t0, P, site)) return false;
     }
 }
 
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         const int4* const stem_g = P.stemseg + (size_t)U.par * (n + 1) * 2;
         auto stem_io = [&](int kx, int& o_in, int& o_z) {
             if (!U.longstem) { o_in = st_in[kx]; o_z = st_z[kx]; }
-            else { int4 w; if (!poll_word(stem_g + (size_t)(U.ns - 1 - kx) * 2, U.seq, w, P)) sh.abort = 1; o_in = w.x; o_z = w.y; }
+            else { int4 w; if (!poll_word(stem_g + (size_t)(U.ns - 1 - kx) * 2, U.seq, w, P, 3)) sh.abort = 1; o_in = w.x; o_z = w.y; }
         };
         nx = x; ndp = dp;
         if ((unsigned)(x - U.a) < (unsigned)U.s) {
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 // 16-byte words of the same lines.  Word 0 says whether the owner has candidates at all; only then are words 1-4 read.
                 const int4* const wbase = P.cyc + ((size_t)par * kRepCyc + cta % kRepCyc) * 5 * Gp + NP + tid;
                 int4 w0;
-                if (!poll_word(wbase, seq, w0, P)) sh.abort = 1;
+                if (!poll_word(wbase, seq, w0, P, 4)) sh.abort = 1;
                 else {
                     const int f = w0.x;
                     c = f & 0xffff;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 #pragma unroll
                             for (int i = 0; i < 4; ++i) w[i] = ld_mail(wbase + (size_t)(i + 1) * Gp);
                             if (w[0].w == seq && w[1].w == seq && w[2].w == seq && w[3].w == seq) break;
-                            if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                            if (spin_check(spins, t0, P, 5)) { sh.abort = 1; break; }
                         }
                         if (f & (1 << 18)) { b1.d = mk64(w[0].x, w[0].y); b1.in = w[0].z; b1.sz = w[1].x; b1.pd = w[1].y; b1.dp = w[1].z; b1.zero = (f >> 16) & 1; }
                         if (f & (1 << 19)) { b2.d = mk64(w[2].x, w[2].y); b2.in = w[2].z; b2.sz = w[3].x; b2.pd = w[3].y; b2.dp = w[3].z; b2.zero = (f >> 17) & 1; }
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             if (!kPricer && !longstem) {
                 for (int q = tid; q < ns; q += kTT) {
                     int4 w[2];
-                    if (!poll_rec<2>(stem_g + (size_t)q * 2, seq, w, P)) sh.abort = 1;
+                    if (!poll_rec<2>(stem_g + (size_t)q * 2, seq, w, P, 6)) sh.abort = 1;
                     const int kx = ns - 1 - q;
                     st_in[kx] = w[0].x; st_z[kx] = w[0].y; st_pd[kx] = w[0].z; st_fl[kx] = mk64(w[1].x, w[1].y); st_up[kx] = w[1].z;
                 }
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         // BlockSearchPivot fields (NS.cs:1294-1302)
         int next_arc = 0, B = P.block_size;
         int ticket = 0, last_tk = 0;                     // last staging request issued; the one before it
+        int tag = 0;                                     // rounds posted so far (the tag of the last one)
         // Staging area.  A block [cursor, cursor + cnt) of the arc arrays is laid out in POSITIONS so that every array is copied as
         // aligned 128-bit words: piece 1 = arcs up to the end of the arrays at positions d0 .., piece 2 (after the wrap) at p2 ..;
         // positions that hold no arc of the block are neutral (state 0).
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
                 if (probes) PROBE(6);
                 if (!__syncthreads_or(missing != 0)) return true;
-                if (spin_check(spins, t0, P)) sh.abort = 1;
+                if (spin_check(spins, t0, P, 7)) sh.abort = 1;
                 if (__syncthreads_or(sh.abort)) return false;
             }
         };
@@ -573,19 +577,20 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         };
 
         // warp 0: read every pricer's record of round r of this pivot; 1 = the round has a winner (written to sh.win), 0 = none
-        auto read_records = [&](int par, int seq, int r) -> int {
+        // (every word of a record carries the TAG of the round it was posted for - rounds are numbered through the whole solve, the
+        // same in every CTA - so that words of two rounds of one pivot can never be taken for one record)
+        auto read_records = [&](int par, int tg) -> int {
             const int4* const line = P.ent + ((size_t)par * kRepEnt + cta % kRepEnt) * NP * kMailWords;
             int4 v = make_int4(0, 0, 0, 0);
             unsigned spins = 0; long long t0 = 0;
             for (;;) {
                 if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
-                const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3) >> 1;    // the round of the record this lane's word belongs to
-                const bool ok = lane >= 4 * NP || (v.w == seq && rd == r);
+                const bool ok = lane >= 4 * NP || v.w == tg;
                 if (__all_sync(0xffffffffu, ok)) break;
                 // a pricer that is already a round further has seen only "none" in this one
-                const bool ahead = lane < 4 * NP && v.w == seq && rd > r;
+                const bool ahead = lane < 4 * NP && v.w - tg == 1;
                 if (__any_sync(0xffffffffu, ahead)) return 0;
-                if (spin_check(spins, t0, P)) { sh.abort = 1; return 0; }
+                if (spin_check(spins, t0, P, 8)) { sh.abort = 1; return 0; }
             }
             const int arc = __shfl_sync(0xffffffffu, v.x, (lane & ~3));
             const int st = __shfl_sync(0xffffffffu, v.x, (lane & ~3) | 1);
@@ -613,8 +618,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // Round 0 is staged (see above); when it is not (mispredicted place, first pivots) and in later rounds (one pivot in ten)
             // the block is requested, staged and collected here.  After each round the pricers post their candidates; everybody
             // (pricers and owners) reads all of them and picks the same winner: smallest reduced cost, then first in scan order.
-            int search_end = 0, nrep = 0, win_round = 0;
+            int search_end = 0, nrep = 0, win_tag = 0;
             bool have_win = false, win_read = false;                  // win_read: sh.win holds the winner already
+            bool explicit_req = false;                                // this search posted an explicit staging request
             for (int r = 0;; ++r) {
                 const long long o_lo = (long long)r * B;
                 const int cnt = (int)min((long long)B, (long long)S - o_lo);
@@ -623,6 +629,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 nrep = (int)(unsigned)(k - 1) - (h ? hb_basis1 : hb_basis0);
                 if (!(r == 0 && (h ? hb_ok1 : hb_ok0) && (h ? hb_cur1 : hb_cur0) == cur && (h ? hb_cnt1 : hb_cnt0) == cnt && (unsigned)nrep <= 2u && sg_cursor == cur && sg_cnt == cnt)) {
                     ++ticket;
+                    explicit_req = true;
                     __syncthreads();                                        // the staging area is no longer read
                     post_request(par, seq, cur, cnt, ticket, 2);
                     layout(cur, cnt);
@@ -682,10 +689,10 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     w_rcb += replay_end(w_ins, nrep); w_rcb -= replay_end(w_int, nrep);
                     const long long w_up = pf_up[w_p];
                     sh.pk[warp] = make_longlong2(bk, bp);
-                    sh.crec[warp][0] = make_int4(pos_arc(w_p), pf_src[w_p], pf_tgt[w_p], seq);
-                    sh.crec[warp][1] = make_int4(pf_st[w_p], w_ins, w_int, seq);
-                    sh.crec[warp][2] = make_int4(lo32(w_rcb), hi32(w_rcb), w_p, seq);
-                    sh.crec[warp][3] = make_int4(lo32(w_up), hi32(w_up), r * 2 + (last_round ? 1 : 0), seq);
+                    sh.crec[warp][0] = make_int4(pos_arc(w_p), pf_src[w_p], pf_tgt[w_p], tag + 1);
+                    sh.crec[warp][1] = make_int4(pf_st[w_p], w_ins, w_int, tag + 1);
+                    sh.crec[warp][2] = make_int4(lo32(w_rcb), hi32(w_rcb), w_p, tag + 1);
+                    sh.crec[warp][3] = make_int4(lo32(w_up), hi32(w_up), last_round ? 1 : 0, tag + 1);
                 }
                 __syncthreads();
                 if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
@@ -693,14 +700,17 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 const longlong2 q = sh.pk[lane & (kTW - 1)];
                 const int ww = warp_argmin(lane < kTW && q.y >= 0, q.x, (int)q.y);      // (every warp computes it: `mine` is needed by all)
                 const bool mine = ww >= 0;
+                ++tag;                                                       // the tag of this round
                 if (warp == 0 && lane < 4 * kRepEnt) {
                     const int wd = lane & 3;
-                    int4 o = mine ? sh.crec[ww][wd] : (wd == 3 ? make_int4(0, 0, r * 2 + (last_round ? 1 : 0), seq) : make_int4(-1, 0, 0, seq));
+                    int4 o = mine ? sh.crec[ww][wd] : (wd == 3 ? make_int4(0, 0, last_round ? 1 : 0, tag) : make_int4(-1, 0, 0, tag));
                     st_mail(P.ent + (((size_t)par * kRepEnt + (lane >> 2)) * NP + cta) * kMailWords + wd, o);
                 }
                 PROBE(0);
-                win_round = r;
-                if (mine) {                                                                // this round has a winner (which one is read later)
+                win_tag = tag;
+                // (pricer 0 after an explicit request reads the records at once: the request word may only be overwritten - by the next
+                // request - when every pricer has collected what the owners served for this one, i.e. has posted its record)
+                if (mine && !(explicit_req && cta == 0)) {                                 // this round has a winner (which one is read later)
                     have_win = true; search_end = (int)(o_lo + cnt);
                     if (NP == 1) {
                         if (tid == 0) { const int4 c0 = sh.crec[ww][0], c1 = sh.crec[ww][1], c2r = sh.crec[ww][2], c3r = sh.crec[ww][3];
@@ -711,7 +721,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 }
                 // no candidate here: did another pricer find one?
                 if (warp == 0) {
-                    const int outcome = read_records(par, seq, r);
+                    const int outcome = read_records(par, tag);
                     if (lane == 0) sh.mode = outcome;
                 }
                 __syncthreads();
@@ -775,7 +785,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 prefetch_l2(P.src + idx); prefetch_l2(P.tgt + idx); prefetch_l2(P.cost + idx); prefetch_l2(P.state + idx);
                 prefetch_l2(P.upper + idx); prefetch_l2(P.upper + min(idx + 16, S - 1));
             }
-            if (!win_read && warp == 0) read_records(par, seq, win_round);  // (the other pricers' candidates have long arrived)
+            if (!win_read && warp == 0) read_records(par, win_tag);         // (the other pricers' candidates have long arrived)
             __syncthreads();
             if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
             const Ent E = sh.win;
@@ -805,6 +815,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     } else {
         // ========================================================================================== the owner CTAs
         int ticket = 0;                                  // last staging request served
+        int etag = 0;                                    // rounds of the pricers consumed so far (see read_records)
         // serve a staging request: for every end of arcs [cursor, cursor + cnt) that this CTA owns, write {pi, in, ticket} - the
         // node's record as of the basis this CTA holds right now - into the pricer's staging slots
         auto serve = [&](int cursor, int cnt, int tk) {
@@ -857,9 +868,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         // lanes [0, 4 NP): word (lane & 3) of pricer (lane >> 2)'s record; lane 4 NP: the staging request (pricer 0's word 4)
                         if (lane < 4 * NP) v = ld_mail(line + (lane >> 2) * kMailWords + (lane & 3));
                         else if (lane == 4 * NP) v = ld_mail(line + 4);
-                        const int rd = __shfl_sync(0xffffffffu, v.z, (lane & ~3) | 3);        // round * 2 + last-round flag of this lane's record
-                        const int rd0 = __shfl_sync(0xffffffffu, rd, 0);
-                        const bool ok = lane >= 4 * NP || (v.w == seq && rd == rd0);
+                        const int rd0 = __shfl_sync(0xffffffffu, v.z, 3);                    // last-round flag (the same in every record of a round)
+                        const bool ok = lane >= 4 * NP || v.w == etag + 1;
+                        // the pricers are further than this CTA thought (rounds whose blocks hold none of its nodes pass without it):
+                        // everything before the newest tag on display found nothing
+                        const int lead = __reduce_max_sync(0xffffffffu, lane < 4 * NP ? v.w - (etag + 1) : 0);
+                        if (lead > 0) { etag += lead; continue; }
                         if (__all_sync(0xffffffffu, ok)) {
                             // every record is of this pivot and of the same round: the one with the smallest reduced cost, then the first
                             // in scan order, is the entering arc; none at all = the round found nothing (the last round: optimal)
@@ -872,12 +886,15 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                                 const int b0 = best >= 0 ? best : 0;
                                 const int4 w = make_int4(__shfl_sync(0xffffffffu, v.x, b0 + (lane & 3)), __shfl_sync(0xffffffffu, v.y, b0 + (lane & 3)), __shfl_sync(0xffffffffu, v.z, b0 + (lane & 3)), seq);
                                 if (lane < 4) sh.ent[lane] = best >= 0 ? w : make_int4(-1, 0, 0, seq);
+                                ++etag;
                                 mode = 1; break;
                             }
+                            ++etag;                                        // nothing in this round, and it was not the last one
+                            continue;
                         }
                         const int4 rq = make_int4(__shfl_sync(0xffffffffu, v.x, 4 * NP), __shfl_sync(0xffffffffu, v.y, 4 * NP), __shfl_sync(0xffffffffu, v.z, 4 * NP), __shfl_sync(0xffffffffu, v.w, 4 * NP));
                         if (rq.w == seq && rq.z != ticket) { if (lane == 0) sh.ent[4] = rq; mode = 2; break; }
-                        if (spin_check(spins, t0, P)) { mode = 3; break; }
+                        if (spin_check(spins, t0, P, 9)) { mode = 3; break; }
                     }
                     if (mode == 1 && lane == 0) sh.ent[4] = make_int4(0, 0, 0, 0);             // (the request that comes with ENTER is fetched after the scan)
                     if (lane == 0) sh.mode = mode;
@@ -1014,7 +1031,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     for (;;) {
                         v = ld_mail(line + 4);
                         if (v.w == seq && (v.z & 3) != 2) break;
-                        if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
+                        if (spin_check(spins, t0, P, 10)) { sh.abort = 1; break; }
                     }
                     sh.ent[4] = v;
                 }
@@ -1059,7 +1076,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     if (!longstem) { p_z = st_z[kx - 1]; p_pd = st_pd[kx - 1]; p_up = st_up[kx - 1]; p_fl = st_fl[kx - 1]; }
                     else {
                         int4 w[2];
-                        if (!poll_rec<2>(stem_g + (size_t)(ns - kx) * 2, seq, w, P)) sh.abort = 1;
+                        if (!poll_rec<2>(stem_g + (size_t)(ns - kx) * 2, seq, w, P, 11)) sh.abort = 1;
                         p_z = w[0].y; p_pd = w[0].z; p_fl = mk64(w[1].x, w[1].y); p_up = w[1].z;
                     }
                     const int npd = p_pd ^ 1;
