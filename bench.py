@@ -99,11 +99,36 @@ def cpu_sample(p, k, prefix, scale=1.0):
         st = oracle.State.load(ck[len(ck) // 2]); start = st.iterations
         r, *_ = oracle.solve(p, pivot_rule=oracle.BLOCK_SEARCH, config=cfg, max_pivots=start + mid // 4, resume=st, emulate_stackalloc=True)
         wins[1 + len(ck) // 2]["us_per_pivot_with_reference_stackalloc"] = 1e6 * r.loop_seconds / max(r.iterations - start, 1)
-    # each window stands for the stretch of the solve up to the next window's start
+    # each window stands for the stretch of the solve up to the next window's start ...
     starts = [w["from_pivot"] for w in wins] + [total]
     est_seconds = sum(w["seconds"] / w["pivots"] * (starts[i + 1] - starts[i]) for i, w in enumerate(wins))
+    # ... or, better, when the cost profile of one full solve on this pool's hosts is on record (profiles/r02_cpu_full_20.json): every
+    # 100 000-pivot bucket of that profile is scaled by (cost per pivot measured now) / (cost per pivot on record) of the window it
+    # belongs to.  A step function through four windows misses how steeply the last sixth of the solve climbs (115 -> 210 us per pivot).
+    prof = recorded_profile(p.name)
+    if prof:
+        def rec_cost(a, b):                                            # recorded seconds per pivot over pivots [a, b)
+            sec = piv = 0.0
+            for bk in prof:
+                lo, hi = max(a, bk["from_pivot"]), min(b, bk["from_pivot"] + bk["pivots"])
+                if hi > lo:
+                    sec += bk["seconds"] * (hi - lo) / bk["pivots"]; piv += hi - lo
+            return sec / piv if piv else None
+        ratios = []
+        for w in wins:
+            rc = rec_cost(w["from_pivot"], w["from_pivot"] + w["pivots"])
+            ratios.append((w["seconds"] / w["pivots"]) / rc if rc else 1.0)
+            w["cost_vs_recorded_profile"] = ratios[-1]
+        est2 = 0.0
+        for bk in prof:
+            i = max(j for j in range(len(wins)) if starts[j] <= bk["from_pivot"])
+            est2 += bk["seconds"] * ratios[i]
+        for w in wins:
+            w["step_estimate_seconds"] = est_seconds
+        est_seconds = est2
+    how = "each scaling its part of the recorded cost profile of one full solve (profiles/r02_cpu_full_20.json)" if prof else "each weighted by the stretch of the solve it stands for"
     desc = (f"{len(wins)} windows of one solve ({', '.join(str(w['pivots']) + ' pivots from pivot ' + str(w['from_pivot']) for w in wins)}; "
-            f"mid-solve windows resume checkpoints the same code wrote), each weighted by the stretch of the {total}-pivot solve it stands for")
+            f"mid-solve windows resume checkpoints the same code wrote), {how}; {total} pivots")
     return total / est_seconds, desc, wins
 
 
@@ -196,6 +221,15 @@ def recorded_full_cpu(name):
     return {"recorded_full_solve": {"oracle_port_s": o.get("loop_seconds"), "oracle_port_pivots_per_s": o.get("pivots_per_s"),
                                     "lemon_1_3_1_run_s": l.get("run_seconds"), "pivots": o.get("pivots"), "host": d.get("host"),
                                     "where": "host cores of a B200 box of this pool, profiles/r02_cpu_full_20.json"}}
+
+
+def recorded_profile(name):
+    path = os.path.join(ROOT, "profiles", "r02_cpu_full_20.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get("oracle_port", {}).get("profile") if d.get("instance") == name else None
 
 
 def recorded_cpu():
@@ -321,7 +355,7 @@ def run_ours(args):
     for _ in range(args.steps):
         piv, kus, launches, h2d, d2h = step()
         tot_piv += piv; tot_kus += kus; tot_h2d += h2d; tot_d2h += d2h; tot_launch += launches
-        if dist is not None:
+        if dist is not None or args.gather:
             g_ms, gathered_n = gather()
             gather_ms += g_ms
     barrier()
@@ -374,7 +408,7 @@ def run_ours(args):
         "gpu_launches": int(launch_all),
         "result_gather": ({"ms_per_step_rank0": gather_ms / args.steps, "records_on_rank0": gathered_n, "bytes_per_record": 8 * width,
                            "what": "NCCL gather of {status, pivots, cost, flow[m], pi[n]} from every rank's device arrays; checksums re-verified on rank 0"}
-                          if dist is not None else None),
+                          if (dist is not None or args.gather) else None),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ns_price_sweep_kernel (Best Eligible full scan, 16 B/arc x S arcs per launch)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -436,6 +470,7 @@ def main():
     ap.add_argument("--workload", default="netgen20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--concurrency", type=int, default=4, help="batch workloads: solves side by side per GPU")
+    ap.add_argument("--gather", action="store_true", help="run the result-record packing / gather also at N = 1 (it always runs at N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
