@@ -1,0 +1,145 @@
+// mcf_device.cuh - device-side data layout shared by the kernels and the host layer of libmcfgpu.
+//
+// The reference keeps the spanning tree as parent/pred/thread/rev_thread/succ_num/last_succ linked lists
+// (DataStructures/SpanningTree.cs:41-45) and walks them one node at a time.  On a GPU a dependent L2 load
+// costs ~130 ns, so a 100-step walk is already slower than a CPU.  This engine therefore replaces the
+// *unobservable* part of that structure (thread, rev_thread, last_succ, succ_num) by a nested-interval
+// labelling: every node u carries in[u] = its index in a depth-first order of the current basis tree and
+// sz[u] = the size of its subtree, so "v is in the subtree of u" is the O(1) test
+// in[u] <= in[v] < in[u] + sz[u].  With that test every per-pivot step of NetworkSimplex.cs:925-1209 becomes a
+// flat data-parallel pass over the node arrays (cycle discovery, leaving-arc arg-min, re-labelling,
+// potential update) instead of a pointer chase.  Only parent / pred / pred_dir / flow / state / pi are
+// semantically observable, and they are maintained exactly as the reference maintains them.
+#pragma once
+#include <stdint.h>
+
+namespace mcf {
+
+constexpr int kThreads = 1024;          // threads per CTA of the persistent pivot kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kListSmem = 3584;         // cycle entries staged in shared memory (32 B each = 112 KB); longer cycles are read from global memory
+constexpr int kStemCap = 2048;          // longest stem (u_in .. u_out) ranked in shared memory; longer ones go through global scratch
+
+// SpanningTree.cs:53-71
+constexpr int STATE_UPPER = -1, STATE_TREE = 0, STATE_LOWER = 1;
+
+// SolverStatus.cs:7-34 (+ engine-internal codes >= 100 that the host turns into error returns)
+enum : int {
+    ST_NOT_SOLVED = 0, ST_OPTIMAL = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_UNBALANCED = 4,
+    ST_ERR_CYCLE_TOO_LONG = 100, ST_ERR_BARRIER_TIMEOUT = 101, ST_ERR_STEM_TOO_LONG = 102, ST_STOPPED_EARLY = 103,
+    ST_ERR_NEEDS_WIDE = 104             // team engine, narrow mode: a tree-arc flow left the int32 range (host re-runs wide)
+};
+
+// pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599; 4 = BlockSearchPivotOptimized,
+// Internal/BlockSearchPivotOptimized.cs:39-157)
+enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3, PK_BLOCK_OPT = 4 };
+
+struct __align__(16) PriceRec {         // one pricing candidate (per CTA, per round)
+    long long c;                        // reduced cost (negative when valid, 0 = none)
+    int arc, src, tgt, cost;
+    int state, off;                     // off = scan offset from next_arc (Block/First)
+};
+
+struct __align__(16) CycEnt {           // one tree node of the pivot cycle, captured before any update
+    int u, in, sz, pd;                  // pd = pred_arc * 2 + (pred_dir == DIR_UP)
+    long long flow, d;                  // flow on pred arc, residual in cycle direction
+};
+
+struct Ctl {                            // control block in global memory (zeroed before launch)
+    unsigned long long bar;             // monotonically increasing grid-barrier counter
+    int abort;                          // set by a barrier time-out
+    int list_count[2];                  // cycle-list fill, double buffered by pivot parity
+    int status;
+    int final_block_size;
+    int infeasible;                     // CheckFeasibility, NS.cs:1272-1283
+    int needs_wide;                     // team engine, narrow mode: a tree-arc flow left the int32 range
+    int pad0;
+    long long iterations;
+    long long arcs_checked;             // SolverMetrics.TotalArcsChecked
+    long long total_cost;               // GetTotalCost, NS.cs:452-465
+    long long degenerate;               // pivots with delta == 0
+    long long cycle_nodes;              // sum of cycle lengths (tree nodes)
+    long long moved_nodes;              // sum of re-hung subtree sizes
+    long long max_cycle, max_stem;
+    long long pricing_rounds;           // grid-wide pricing rounds (each = one barrier)
+    unsigned long long ns_price, ns_cycle, ns_update, ns_total;   // %globaltimer deltas seen by CTA 0
+    unsigned long long ns_wait_done, ns_wait_cyc, ns_stem;        // team engine: hop waits of the pricing CTA
+    long long stem_exchanges;                                     // team engine: pivots that needed the stem exchange
+    unsigned long long clk_total;                                 // team engine: clock64 ticks over the loop (phase accumulators are ticks)
+    unsigned long long clk[16];                                   // team engine: sub-phase tick accumulators (0-7 pricing CTA, 8-15 owner CTA 1)
+    long long arcs_priced_opt;                                    // flat engine, PK_BLOCK_OPT: arcs priced (the reference keeps no counter there)
+};
+
+struct Params {
+    int n, m, S, A;                     // nodes, arcs, search arcs (m+n), allocated arcs
+    // arcs
+    const int* src; const int* tgt; const int* cost;     // [S]
+    int* state;                                          // [A]
+    long long* flow;                                     // [A]
+    const long long* upper;                              // [A]
+    const long long* orig_lower;                         // [m] or nullptr (restored into flow at the end)
+    long long* rc_cache;                                 // [S] or nullptr (PK_BLOCK_CACHED)
+    // nodes, [n+1] (root = n)
+    int* in; int* sz; int* parent; int* pd;
+    long long* pi;
+    // work areas
+    PriceRec* part;                     // [2][gridDim.x]
+    CycEnt* list; int list_cap;
+    int* stem_scratch;                  // [6][n+1] flat engine: stems longer than kStemCap are ranked and read here
+    Ctl* ctl;
+    // pricing configuration (BlockSearchPivot ctor, NS.cs:1304-1337; adaptive rule :1399-1438)
+    int kind;
+    int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
+    double low_thr, high_thr, shrink, grow;
+    int lookahead0;                     // groups priced in the first round of a search
+    int simd_width;                     // PK_BLOCK_OPT: Vector<long>.Count of the host the reference would run on (0 = scalar path)
+    long long max_iterations;           // NS.cs:280
+    long long stop_after;               // >0: stop after this many pivots (bounded samples / tests)
+    unsigned long long barrier_timeout_cycles;
+};
+
+// ------------------------------------------------------------------------------------------------ team engine
+// (mcf_team.cu) node slices resident in shared memory, CTAs exchange 16-byte self-validating words through L2.
+
+constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
+constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
+constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages in shared memory (longer ones are read in place)
+constexpr int kStageMax = 3584;         // arcs of one pricing block staged in the pricing CTAs' shared memory (= largest block size)
+constexpr int kReqMax = 16384;          // arcs per explicit staging request (later rounds of a search)
+
+// per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
+constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32;
+
+struct TeamParams {
+    int n, m, S, A;
+    const int* src; const int* tgt; const int* cost;     // [S]
+    int* state;                                          // [A]   read and written by the pricing CTA only
+    long long* flow;                                     // [A]
+    const long long* upper;                              // [A]
+    const long long* orig_lower;                         // [m] or nullptr
+    long long* pi;                                       // [n+1] potentials (NS.cs:48); every entry is read and written by its owner CTA only
+    const int* in0; const int* sz0; const int* pd0; const int* dp0;   // [n+1] initial basis: depth-first index, subtree size, pred word, depth
+    int4* ent;                                           // [2][kRepEnt][pricers][kMailWords] pricer -> all: its candidate of the round; pricer 0 also the staging requests
+    int4* cyc;                                           // [2][kRepCyc][5][team padded to 8] owner -> all: leaving-arc candidates, word-major
+    int4* stemseg;                                       // [2][n+1][2]                     stem entries, indexed by depth
+    int4* stage;                                         // [2 * kReqMax]                   owner -> pricer: {pi, in} of the arc ends of a requested range
+    Ctl* ctl;
+    int team;                                            // CTAs: [0, pricers) price, [pricers, team) own node slices
+    int pricers;
+    int slice;                                           // nodes per owner
+    int wide;                                            // 1: tree-arc flows / capacities resident as int64, 0: int32
+    int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
+    double low_thr, high_thr, shrink, grow;
+    long long max_iterations, stop_after;
+    unsigned long long timeout_cycles;
+};
+
+// SolutionValidator on the device (mcf_kernels.cu)
+struct ValidateParams {
+    int n, m, supply_type;
+    const int* src; const int* tgt; const int* cost;
+    const long long* flow; const long long* lower; const long long* upper; const long long* supply; const long long* pi;
+    long long* net; long long* adj; long long* out;
+};
+
+}  // namespace mcf
