@@ -422,11 +422,11 @@ def run_ours(args):
                          "arcs_priced_per_pivot": M.arcs_priced / max(M.iterations, 1),
                          # in-kernel probes of the team engine (clock64 deltas of one pricing CTA and of the first owner CTA), us per pivot
                          "pricer_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
-                             ("price_all_rounds", 0), ("cursor_post_ENTER_start_staging", 1), ("collect_node_records_of_next_block", 2),
-                             ("finish_staging", 3), ("wait_and_gather_CYC", 4), ("decide_and_state_update", 5))} if M.engine == 2 else None,
+                             ("price_and_post_ENTER", 1), ("collect_ENTER", 2), ("stage_next_block_arcs", 3), ("wait_DONE", 6), ("finish_staging", 0),
+                             ("gather_node_records_post_GATHERED", 7), ("wait_and_gather_CYC", 4), ("decide", 5))} if M.engine == 2 else None,
                          "owner_cta_us": {nm: M.phase_us[i] / max(M.iterations, 1) for nm, i in (
-                             ("wait_ENTER", 9), ("scan_slice", 10), ("reduce_and_post_CYC", 11), ("serve_staging_request", 8),
-                             ("gather_CYC_and_decide", 12), ("cycle_node_update", 15), ("relabel", 13), ("end_of_pivot_barrier", 14))} if M.engine == 2 else None,
+                             ("wait_and_collect_ENTER", 9), ("scan_slice", 10), ("reduce_and_post_CYC", 11), ("gather_CYC_and_decide", 12),
+                             ("cycle_node_update", 15), ("relabel", 13), ("post_DONE", 14))} if M.engine == 2 else None,
                          "pricing_GBps_in_kernel": M.pricing_bytes / max(M.pivot_search_time_us, 1e-9) / 1e3},
     }
     # CPU baseline (oracle port) on a bounded sample + the GPU on the very same sample
@@ -450,12 +450,6 @@ def run_ours(args):
             ns._dirty = True
             out["cpu_baseline"]["gpu_same_sample"] = {"pivots": Ms.iterations, "kernel_pivots_per_s": Ms.iterations / (Ms.kernel_time_us * 1e-6),
                                                       "e2e_pivots_per_s": Ms.iterations / gw}
-        rec = recorded_cpu()
-        name = probs[0].name
-        if rec and name in rec:
-            out["cpu_baseline"]["recorded_full_solve"] = {
-                "oracle_port_s": rec[name].get("oracle_loop_seconds"), "lemon_1_3_1_s": rec[name].get("lemon_seconds"),
-                "pivots": rec[name].get("pivots"), "where": "build container (8 vCPU Xeon, shared), tests/golden/large.json"}
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()

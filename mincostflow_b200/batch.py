@@ -44,7 +44,7 @@ class _DeviceArray:
     """Zero-copy view of `count` int64 values at a raw device pointer (`__cuda_array_interface__`)."""
 
     def __init__(self, ptr: int, count: int):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (ptr, True), "version": 3, "strides": None}
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
 
 
 def device_result_tensors(ns):

@@ -91,15 +91,31 @@ struct mcf_handle {
     const long long* d_pi_final = nullptr;                            // potentials of the last solve, device side
     int supply_type_solved = 0;
     // team engine (mcf_team.cu)
-    DevBuf<int4> d_mail;                                              // ent | cyc | stage | stemseg
-    DevBuf<int> d_dp;
-    std::vector<int> h_dp;
+    DevBuf<mcf::NodeRec> d_node;
+    DevBuf<int4> d_mail;                                              // ent0 | prc | late | cyc | stemseg
+    DevBuf<unsigned> d_done;
+    DevBuf<long long> d_piout;
+    std::vector<mcf::NodeRec> h_node;
     // host staging for the initial basis
     std::vector<int> h_src, h_tgt, h_cost, h_state, h_in, h_sz, h_parent, h_pd;
     std::vector<long long> h_flow, h_upper, h_pi;
 };
 
 namespace {
+
+// The persisting-L2 set-aside is a device-wide limit, and changing it waits for the kernels that are running on the device:
+// with several solves side by side (mcf_solve_batch_concurrent) a per-solve cudaDeviceSetLimit serialised them.  It is
+// therefore only ever raised, under a lock, and the batch entry point raises it once before its workers start.
+std::mutex g_persist_mu;
+size_t g_persist_limit[64] = {0};
+void ensure_persisting_l2(int device, size_t want)
+{
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lk(g_persist_mu);
+    if (g_persist_limit[device] >= want) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) g_persist_limit[device] = want;
+    else cudaGetLastError();
+}
 
 int fail(mcf_handle* h, int code, const char* fmt, ...)
 {
@@ -225,7 +241,7 @@ int bind_device(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_mail.release(); h->d_dp.release(); h->d_val.release(); h->d_pi_final = nullptr;
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->device_bound = dev;
     }
@@ -237,7 +253,7 @@ int bind_device(mcf_handle* h)
 void build_initial_basis(mcf_handle* h, int64_t art_cost)
 {
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n, root = n;
-    h->h_src.assign(S + 4, 0); h->h_tgt.assign(S + 4, 0); h->h_cost.assign(S + 4, 0);   // four zero entries behind the arrays: the team engine reads aligned 128-bit words
+    h->h_src.assign(S, 0); h->h_tgt.assign(S, 0); h->h_cost.assign(S, 0);
     h->h_state.assign(A, mcf::STATE_LOWER); h->h_flow.assign(A, 0); h->h_upper.assign(A, kInf);
     h->h_in.resize(n + 1); h->h_sz.resize(n + 1); h->h_parent.resize(n + 1); h->h_pd.resize(n + 1); h->h_pi.assign(n + 1, 0);
     for (int e = 0; e < m; ++e) {
@@ -317,13 +333,12 @@ int choose_grid(mcf_handle* h, int* sms_out)
 }
 
 
-// Team engine (mcf_team.cu): CTA 0 prices, the others own node slices that stay in shared memory.
+// Team engine (mcf_team.cu): the first `pricers` CTAs price, the others own node slices that stay in shared memory.
 // Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine).
-int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out, int* pricers_out)
+int choose_team(mcf_handle* h, int wide, int* slice_out, int* pricers_out)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->opt.device) != cudaSuccess) return 0;
-    if (max_block > mcf::kStageMax) return 0;                                   // the pricing CTA stages one whole block in shared memory
     const int max_slice = mcfk_team_max_slice(h->opt.device, wide);
     if (max_slice <= 0) return 0;
     int limit = prop.multiProcessorCount;
@@ -331,14 +346,16 @@ int choose_team(mcf_handle* h, int wide, int max_block, int* slice_out, int* pri
     if (h->opt.max_ctas > 1 && h->opt.max_ctas < limit) limit = h->opt.max_ctas;
     if (limit < 2) return 0;
     const long long nodes = (long long)h->n + 1;
+    const long long S = (long long)h->m + h->n;
     const long long need = (nodes + max_slice - 1) / max_slice;                 // owners the slices need at least
-    // pricers: the block is split over them (each stages, collects and prices its share); about 768 arcs each, at most 4
-    // (mcf_options.lookahead_blocks > 0 sets their number, up to 6)
-    long long pricers = h->opt.lookahead_blocks > 0 ? std::min(h->opt.lookahead_blocks, 6) : std::min((max_block + 767) / 768, 4);
+    if (need > limit - 1) return 0;
+    // pricers: one SM is gather-bound on a whole block; ~192 arcs of the first block per pricer (each arc end costs two L1TEX line look-ups)
+    const long long B = (long long)std::sqrt((double)S);
+    long long pricers = h->opt.lookahead_blocks > 0 ? h->opt.lookahead_blocks : (B + 191) / 192;
     if (pricers < 1) pricers = 1;
+    if (pricers > mcf::kMaxPricers) pricers = mcf::kMaxPricers;
     if (pricers > limit - need) pricers = limit - need;
-    if (pricers < 1) return 0;
-    // owners: ~1024 nodes each when SMs are to spare (fewer CTAs make every exchange cheaper), never fewer than needed
+    // owners: ~1024 nodes each when SMs are to spare (fewer CTAs make every hop cheaper), never fewer than needed
     long long owners = (nodes + 1023) / 1024;
     if (owners < need) owners = need;
     if (owners > limit - pricers) owners = limit - pricers;
@@ -356,37 +373,42 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
     CUDA_TRY(h, h->d_state.ensure(A + 4)); CUDA_TRY(h, h->d_flow.ensure(A)); CUDA_TRY(h, h->d_upper.ensure(A));
-    CUDA_TRY(h, h->d_in.ensure(n + 1)); CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1)); CUDA_TRY(h, h->d_dp.ensure(n + 1));
-    CUDA_TRY(h, h->d_pi.ensure(n + 1)); CUDA_TRY(h, h->d_ctl.ensure(1));
+    CUDA_TRY(h, h->d_sz.ensure(n + 1)); CUDA_TRY(h, h->d_pd.ensure(n + 1));
+    // node mirror {pi, depth} and the dense label array live in ONE allocation so that a single L2 access-policy window can
+    // keep both resident (the arc arrays stream through L2 and would otherwise evict them between two uses of a record)
+    const size_t mirror_recs = (size_t)(n + 1) + ((size_t)(n + 1) * 4 + sizeof(mcf::NodeRec) - 1) / sizeof(mcf::NodeRec);
+    CUDA_TRY(h, h->d_node.ensure(mirror_recs));
+    int* const d_in_g = reinterpret_cast<int*>(h->d_node.p + (n + 1));
+    CUDA_TRY(h, h->d_piout.ensure(n)); CUDA_TRY(h, h->d_ctl.ensure(1)); CUDA_TRY(h, h->d_done.ensure((size_t)(team + pricers) * 32));     // DONE flags of the owners + GATHERED flags of the pricers
     int rep_ent = 1, rep_cyc = 1;
     mcfk_team_replicas(&rep_ent, &rep_cyc);
-    const size_t w_ent = (size_t)2 * rep_ent * pricers * mcf::kMailWords;
-    const size_t w_cyc = (size_t)2 * rep_cyc * 5 * ((team + 7) & ~7);           // word-major: [2][replica][word 0..4][team padded to 8]
-    const size_t w_stage = (size_t)2 * mcf::kReqMax;
+    const size_t w_ent = (size_t)2 * rep_ent * pricers * mcf::kMailWords, w_pr = (size_t)2 * pricers * mcf::kMailWords, w_late = 2 * mcf::kMailWords;
+    const size_t w_cyc = (size_t)2 * rep_cyc * team * mcf::kMailWords;
     const size_t w_seg = (size_t)4 * (n + 1);     // [2 parities][n+1 entries][2 words]
-    const size_t seg_off = (w_ent + w_cyc + w_stage + 7) & ~(size_t)7;
+    const size_t seg_off = (w_ent + w_pr + w_late + w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
-    h->h_dp.resize(n + 1);
-    for (int u = 0; u <= n; ++u) h->h_dp[u] = u == n ? 0 : 1;                   // the initial basis is the star around the root
+    h->h_node.resize(n + 1);
+    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = u == n ? 0 : 1; }
     cudaStream_t st = h->stream;
     int64_t bytes = 0;
     auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };
-    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)(S + 4) * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)(S + 4) * 4));
-    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)(S + 4) * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
+    CUDA_TRY(h, up(h->d_src.p, h->h_src.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_tgt.p, h->h_tgt.data(), (size_t)S * 4));
+    CUDA_TRY(h, up(h->d_cost.p, h->h_cost.data(), (size_t)S * 4)); CUDA_TRY(h, up(h->d_state.p, h->h_state.data(), (size_t)A * 4));
     CUDA_TRY(h, up(h->d_flow.p, h->h_flow.data(), (size_t)A * 8)); CUDA_TRY(h, up(h->d_upper.p, h->h_upper.data(), (size_t)A * 8));
-    CUDA_TRY(h, up(h->d_in.p, h->h_in.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4));
-    CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_dp.p, h->h_dp.data(), (size_t)(n + 1) * 4));
-    CUDA_TRY(h, up(h->d_pi.p, h->h_pi.data(), (size_t)(n + 1) * 8));
+    CUDA_TRY(h, up(h->d_sz.p, h->h_sz.data(), (size_t)(n + 1) * 4)); CUDA_TRY(h, up(h->d_pd.p, h->h_pd.data(), (size_t)(n + 1) * 4));
+    CUDA_TRY(h, up(h->d_node.p, h->h_node.data(), (size_t)(n + 1) * sizeof(mcf::NodeRec)));
+    CUDA_TRY(h, up(d_in_g, h->h_in.data(), (size_t)(n + 1) * 4));
     CUDA_TRY(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(mcf::Ctl), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_done.p, 0, (size_t)(team + pricers) * 32 * sizeof(unsigned), st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_mail.p, 0, (seg_off + w_seg + 8) * sizeof(int4), st));
     h->metrics.h2d_bytes = bytes;
     std::memset(P, 0, sizeof(*P));
     P->n = n; P->m = m; P->S = S; P->A = A;
     P->src = h->d_src.p; P->tgt = h->d_tgt.p; P->cost = h->d_cost.p; P->state = h->d_state.p; P->flow = h->d_flow.p; P->upper = h->d_upper.p;
-    P->pi = h->d_pi.p; P->in0 = h->d_in.p; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->dp0 = h->d_dp.p;
-    P->ent = h->d_mail.p; P->cyc = P->ent + w_ent; P->stage = P->cyc + w_cyc;
+    P->node = h->d_node.p; P->in_g = d_in_g; P->sz0 = h->d_sz.p; P->pd0 = h->d_pd.p; P->pi_out = h->d_piout.p;
+    P->ent0 = h->d_mail.p; P->prc = P->ent0 + w_ent; P->late = P->prc + w_pr; P->cyc = P->late + w_late;
     P->stemseg = h->d_mail.p + seg_off;
-    P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
+    P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
     return MCF_OK;
 }
 
@@ -419,6 +441,23 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     const double tmo = h->opt.barrier_timeout_s > 0 ? h->opt.barrier_timeout_s : 10.0;
     P.timeout_cycles = (unsigned long long)(tmo * 1.9e9);
 
+    {   // keep the node mirror L2-resident (persisting lines), everything else on this stream streams through
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, h->opt.device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->opt.device);
+        const size_t mirror_bytes = (size_t)(n + 1) * (sizeof(mcf::NodeRec) + 4);
+        if (max_win > 0 && max_persist > 0) {
+            const size_t want = std::min<size_t>(mirror_bytes + (1u << 20), (size_t)max_persist);
+            ensure_persisting_l2(h->opt.device, want);
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = h->d_node.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(mirror_bytes, (size_t)max_win);
+            av.accessPolicyWindow.hitRatio = mirror_bytes <= want ? 1.0f : (float)((double)want / (double)mirror_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+    }
     EventPair evp;
     CUDA_TRY(h, evp.create());
     const cudaEvent_t ev0 = evp.a, ev1 = evp.b;
@@ -436,12 +475,12 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     CUDA_TRY(h, cudaMemcpyAsync(&ctl, h->d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
     h->flow.resize(m); h->pi.resize(n);
     CUDA_TRY(h, cudaMemcpyAsync(h->flow.data(), h->d_flow.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->pi.data(), h->d_pi.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->pi.data(), h->d_piout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->metrics.d2h_time_us = us_since(t_d2h);
     h->metrics.d2h_bytes = (int64_t)m * 8 + (int64_t)n * 8 + (int64_t)sizeof(ctl);
 
-    if ((ctl.needs_wide || ctl.status == mcf::ST_ERR_NEEDS_WIDE) && !wide) { *needs_wide = true; return MCF_OK; }     // a flow left the int32 range: the caller re-runs wide
+    if (ctl.needs_wide && !wide) { *needs_wide = true; return MCF_OK; }     // a flow left the int32 range: the caller re-runs wide
     mcf_metrics& M = h->metrics;
     M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
@@ -457,9 +496,9 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     M.degenerate_pivots = ctl.degenerate; M.cycle_nodes = ctl.cycle_nodes; M.moved_nodes = ctl.moved_nodes;
     M.max_cycle = ctl.max_cycle; M.max_stem = ctl.max_stem; M.pricing_rounds = ctl.pricing_rounds;
     M.arcs_priced = ctl.arcs_checked; M.pricing_bytes = 16 * M.arcs_priced; M.engine = 2;
-    h->total_cost = ctl.total_cost; h->d_pi_final = h->d_pi.p; h->supply_type_solved = h->opt.supply_type;
+    h->total_cost = ctl.total_cost; h->d_pi_final = h->d_piout.p; h->supply_type_solved = h->opt.supply_type;
 
-    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots (wait site %d of CTA %d)", (long long)ctl.iterations, ctl.pad0 / 1000, ctl.pad0 % 1000); }
+    if (ctl.abort || ctl.status == mcf::ST_ERR_BARRIER_TIMEOUT) { done(MCF_NOT_SOLVED); return fail(h, MCF_ERR_TIMEOUT, "team exchange timed out after %lld pivots", (long long)ctl.iterations); }
     if (ctl.status == mcf::ST_ERR_CYCLE_TOO_LONG || ctl.status == mcf::ST_ERR_STEM_TOO_LONG) {
         done(MCF_NOT_SOLVED);
         return fail(h, MCF_ERR_ENGINE_LIMIT, "pivot %lld: stem exceeds the in-kernel staging buffer (%d entries)", (long long)ctl.iterations, mcf::kTeamStemCap);
@@ -532,7 +571,7 @@ void mcf_destroy(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_mail.release(); h->d_dp.release(); h->d_val.release(); h->d_pi_final = nullptr;
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -658,10 +697,9 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
             int64_t pos = 0;
             for (int u = 0; u < n; ++u) { const int64_t a = h->supply[u] < 0 ? -h->supply[u] : h->supply[u]; pos += a; if (pos >= (int64_t)std::numeric_limits<int32_t>::max()) { wide = 1; break; } }
         }
-        const int max_block = (cfg.flags & MCF_FLAG_ADAPTIVE_BLOCK_SIZE) ? std::max(block, cfg.max_block_size) : block;
         for (; wide < 2; ++wide) {
             int slice = 0, pricers = 0;
-            const int team = choose_team(h, wide, std::min(max_block, S), &slice, &pricers);
+            const int team = choose_team(h, wide, &slice, &pricers);
             if (team <= 0) break;
             bool needs_wide = false;
             rc = solve_team(h, team, pricers, slice, wide, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
@@ -852,6 +890,16 @@ int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* de
     // the SMs (a 2^18-node instance needs 37 CTAs, four run side by side on 148 SMs).  The solves are independent - no kernel
     // ever waits for another one - so they may also simply run one after the other if the SMs are not free.
     const int lanes = n_devices * per_device;
+    if (per_device > 1) {                           // raise the persisting-L2 set-aside once, before any kernel runs (see ensure_persisting_l2)
+        int max_n = 0;
+        for (int i = 0; i < count; ++i) if (hs[i] && hs[i]->n > max_n) max_n = hs[i]->n;
+        for (int d = 0; d < n_devices; ++d) {
+            int max_persist = 0;
+            if (cudaSetDevice(devices[d]) != cudaSuccess || cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, devices[d]) != cudaSuccess) { cudaGetLastError(); continue; }
+            const size_t one = (size_t)(max_n + 1) * (sizeof(mcf::NodeRec) + 4) + (1u << 20);
+            ensure_persisting_l2(devices[d], std::min<size_t>(one * (size_t)per_device, (size_t)max_persist));
+        }
+    }
     std::vector<int> rcs(lanes, MCF_OK);
     std::vector<std::thread> workers;
     for (int w = 0; w < lanes; ++w) {

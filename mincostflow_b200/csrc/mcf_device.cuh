@@ -101,11 +101,17 @@ struct Params {
 // ------------------------------------------------------------------------------------------------ team engine
 // (mcf_team.cu) node slices resident in shared memory, CTAs exchange 16-byte self-validating words through L2.
 
+struct __align__(16) NodeRec {          // global mirror of a node, read by the pricing gathers (one 128-bit load)
+    long long pi;                       // potential (NS.cs:48)
+    int in;                             // initial depth-first index (the live one is the dense array TeamParams::in_g: a third of
+                                        // all labels shift on every pivot, and 4-byte-stride stores cost a quarter of the sectors)
+    int dp;                             // current depth of the node (root = 0)
+};
+
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
-constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages in shared memory (longer ones are read in place)
-constexpr int kStageMax = 3584;         // arcs of one pricing block staged in the pricing CTAs' shared memory (= largest block size)
-constexpr int kReqMax = 16384;          // arcs per explicit staging request (later rounds of a search)
+constexpr int kMaxPricers = 16;         // pricing CTAs of a team
+constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages
 
 // per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
 constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32;
@@ -113,16 +119,20 @@ constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32;
 struct TeamParams {
     int n, m, S, A;
     const int* src; const int* tgt; const int* cost;     // [S]
-    int* state;                                          // [A]   read and written by the pricing CTA only
+    int* state;                                          // [A]
     long long* flow;                                     // [A]
     const long long* upper;                              // [A]
     const long long* orig_lower;                         // [m] or nullptr
-    long long* pi;                                       // [n+1] potentials (NS.cs:48); every entry is read and written by its owner CTA only
-    const int* in0; const int* sz0; const int* pd0; const int* dp0;   // [n+1] initial basis: depth-first index, subtree size, pred word, depth
-    int4* ent;                                           // [2][kRepEnt][pricers][kMailWords] pricer -> all: its candidate of the round; pricer 0 also the staging requests
-    int4* cyc;                                           // [2][kRepCyc][5][team padded to 8] owner -> all: leaving-arc candidates, word-major
-    int4* stemseg;                                       // [2][n+1][2]                     stem entries, indexed by depth
-    int4* stage;                                         // [2 * kReqMax]                   owner -> pricer: {pi, in} of the arc ends of a requested range
+    NodeRec* node;                                       // [n+1] (root = n): pi and depth
+    int* in_g;                                           // [n+1] current depth-first index of every node
+    const int* sz0; const int* pd0;                      // [n+1] initial basis
+    long long* pi_out;                                   // [n]
+    int4* ent0;                                          // [2][pricers][kMailWords]  pricer -> all: its part of the first block
+    int4* late;                                          // [2][kMailWords]           pricer 0 -> all: result of a multi-block search
+    int4* prc;                                           // [2][pricers][kMailWords]  pricer -> pricers: later rounds of a search
+    int4* cyc;                                           // [2][team][kMailWords]     owner -> all
+    int4* stemseg;                                       // [2][n+1][2]               stem entries, owner o at its slice offset
+    unsigned int* done;                                  // [team + pricers][32]      owner -> pricers (DONE), pricer -> owners (GATHERED)
     Ctl* ctl;
     int team;                                            // CTAs: [0, pricers) price, [pricers, team) own node slices
     int pricers;

@@ -2,7 +2,7 @@
 # Round-2 measurement run on one B200 (under gpurun): the bench line of every BASELINE config and the reference arm.
 set -u
 mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 3 > gpurun_out/r02_bench_netgen20.json 2> gpurun_out/r02_bench_netgen20.err; echo "netgen20 rc=$?"
+python bench.py --steps 2 --warmup 3 --gather > gpurun_out/r02_bench_netgen20.json 2> gpurun_out/r02_bench_netgen20.err; echo "netgen20 rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_netgen20.json 2> gpurun_out/r02_bench_reference.err; echo "reference rc=$?"
 for w in netgen10k netgen16 grid1024 "batch18 --gather"; do
   python bench.py --workload $w --steps 1 --warmup 1 > gpurun_out/r02_bench_${w%% *}.json 2> gpurun_out/r02_bench_${w%% *}.err; echo "$w rc=$?"
