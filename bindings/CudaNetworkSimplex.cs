@@ -100,7 +100,8 @@ namespace MinCostFlow.Core.Cuda
 
         public SolverStatus Solve()
         {
-            if (_opt.PivotRule > (int)PivotRule.BlockSearch) throw new NotImplementedException($"Pivot rule {(PivotRule)_opt.PivotRule} not implemented yet");   // NetworkSimplex.cs:884
+            // CandidateList / AlteringList run here (defined as LEMON's, network_simplex.h:413-635); NetworkSimplex.cs:884 throws on them.
+            if (_opt.PivotRule > (int)PivotRule.BlockSearch && _opt.OptimizedPivot != 0) throw new NotImplementedException($"Optimized pivot rule {(PivotRule)_opt.PivotRule} not implemented");   // NetworkSimplex.cs:1694
             fixed (long* lo = _lower, up = _upper, co = _cost, su = _supply)               // pinned for the call only, like OptimizedPivotWrapper (NetworkSimplex.cs:1699-1722)
             {
                 Check(Native.mcf_set_arcs(_h, lo, up, co));

@@ -212,7 +212,9 @@ public:
     // ---- Solve(), :215-411
     SolverStatus Solve() override
     {
-        if (opt_.pivot_rule > (int)PivotRule::BlockSearch) throw NotImplementedException("Pivot rule not implemented yet");   // :884
+        // CandidateList / AlteringList: the reference throws (:884); here they run, defined as LEMON's (network_simplex.h:413-635).
+        // The optimized wrapper still knows only the first three rules (:1689-1695).
+        if (opt_.pivot_rule > (int)PivotRule::BlockSearch && opt_.optimized_pivot) throw NotImplementedException("Optimized pivot rule not implemented");
         Push();
         int32_t st = 0;
         Check(mcf_solve(h_, &st));

@@ -55,7 +55,10 @@ typedef enum mcf_error {
 /* Enum values are the reference's: SolverStatus.cs:7-34, PivotRule.cs:7-40, SupplyType.cs:7-17,
  * OptimizationFlags in OptimizationTypes.cs:8-20. */
 typedef enum mcf_status { MCF_NOT_SOLVED = 0, MCF_OPTIMAL = 1, MCF_INFEASIBLE = 2, MCF_UNBOUNDED = 3, MCF_UNBALANCED = 4 } mcf_status;
-typedef enum mcf_pivot_rule { MCF_FIRST_ELIGIBLE = 0, MCF_BEST_ELIGIBLE = 1, MCF_BLOCK_SEARCH = 2 } mcf_pivot_rule;
+typedef enum mcf_pivot_rule {       /* PivotRule.cs:7-40; 3 and 4 are declared there and thrown on at NetworkSimplex.cs:884 - here they run, defined as
+                                       LEMON's CandidateListPivotRule / AlteringListPivotRule (lemon-1.3.1/lemon/network_simplex.h:413-635) */
+    MCF_FIRST_ELIGIBLE = 0, MCF_BEST_ELIGIBLE = 1, MCF_BLOCK_SEARCH = 2, MCF_CANDIDATE_LIST = 3, MCF_ALTERING_LIST = 4
+} mcf_pivot_rule;
 typedef enum mcf_supply_type { MCF_GEQ = 0, MCF_LEQ = 1 } mcf_supply_type;
 enum {
     MCF_FLAG_ADAPTIVE_BLOCK_SIZE = 1, MCF_FLAG_SMALL_BLOCKS_FOR_DENSE = 2, MCF_FLAG_REDUCED_COST_CACHING = 4,

@@ -85,6 +85,8 @@ struct mcf_handle {
     DevBuf<mcf::PriceRec> d_part;
     DevBuf<mcf::CycEnt> d_list;
     DevBuf<int> d_scratch;                                            // flat engine: stem scratch (mcf_device.cuh)
+    DevBuf<int> d_cand, d_cand_scratch;                               // Candidate List / Altering List rules (mcf_device.cuh)
+    DevBuf<long long> d_cand_cost;
     DevBuf<mcf::Ctl> d_ctl;
     DevBuf<unsigned char> d_flush;
     DevBuf<long long> d_val;                                          // validator scratch
@@ -614,8 +616,12 @@ int mcf_set_options(mcf_handle* h, const mcf_options* opt)
 {
     if (!h || !opt) return MCF_ERR_INVALID_ARGUMENT;
     if (opt->supply_type != MCF_GEQ && opt->supply_type != MCF_LEQ) return fail(h, MCF_ERR_INVALID_ARGUMENT, "unknown supply type %d", opt->supply_type);
-    if (opt->pivot_rule < MCF_FIRST_ELIGIBLE || opt->pivot_rule > MCF_BLOCK_SEARCH)
-        return fail(h, MCF_ERR_INVALID_ARGUMENT, "pivot rule %d not implemented yet", opt->pivot_rule);   // NS.cs:884
+    // The reference throws NotImplementedException for CandidateList / AlteringList (NS.cs:884); here they run, defined as LEMON's
+    // (network_simplex.h:413-635).  The optimized wrapper knows the first three rules only (OptimizedPivotWrapper, NS.cs:851-856).
+    if (opt->pivot_rule < MCF_FIRST_ELIGIBLE || opt->pivot_rule > MCF_ALTERING_LIST)
+        return fail(h, MCF_ERR_INVALID_ARGUMENT, "pivot rule %d does not exist", opt->pivot_rule);
+    if (opt->optimized_pivot && opt->pivot_rule > MCF_BLOCK_SEARCH)
+        return fail(h, MCF_ERR_INVALID_ARGUMENT, "pivot rule %d has no optimized variant", opt->pivot_rule);
     if (opt->simd_width < 0 || opt->simd_width > 64) return fail(h, MCF_ERR_INVALID_ARGUMENT, "simd_width %d out of range", opt->simd_width);
     h->opt = *opt;
     return MCF_OK;
@@ -662,8 +668,20 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     int kind = h->opt.pivot_rule;
     if (!h->opt.optimized_pivot && h->opt.pivot_rule == MCF_BLOCK_SEARCH && (cfg.flags & MCF_FLAG_REDUCED_COST_CACHING)) kind = mcf::PK_BLOCK_CACHED;
     if (h->opt.optimized_pivot && h->opt.pivot_rule == MCF_BLOCK_SEARCH) kind = mcf::PK_BLOCK_OPT;          // NS.cs:851-856
-    int block = 0, dyn_min = 0;
-    if (kind == mcf::PK_BLOCK_OPT) {
+    if (h->opt.pivot_rule == MCF_CANDIDATE_LIST) kind = mcf::PK_CAND_LIST;
+    if (h->opt.pivot_rule == MCF_ALTERING_LIST) kind = mcf::PK_ALT_LIST;
+    int block = 0, dyn_min = 0, list_length = 0, minor_limit = 0, head_length = 0, cand_cap = 0;
+    if (kind == mcf::PK_CAND_LIST) {                                                                  // network_simplex.h:441-458
+        list_length = std::max((int)(0.25 * std::sqrt((double)S)), 10);
+        minor_limit = std::max((int)(0.1 * list_length), 3);
+        cand_cap = list_length;
+        cfg.flags &= ~MCF_FLAG_ADAPTIVE_BLOCK_SIZE;
+    } else if (kind == mcf::PK_ALT_LIST) {                                                            // network_simplex.h:563-580
+        block = std::max((int)(1.0 * std::sqrt((double)S)), 10);
+        head_length = std::max((int)(0.01 * block), 3);
+        cand_cap = head_length + block;
+        cfg.flags &= ~MCF_FLAG_ADAPTIVE_BLOCK_SIZE;
+    } else if (kind == mcf::PK_BLOCK_OPT) {
         block = std::max((int)std::sqrt((double)S), 10);                                              // BlockSearchPivotOptimized.cs:27-28 (MIN_BLOCK_SIZE, NS.cs:100)
         cfg.flags &= ~MCF_FLAG_ADAPTIVE_BLOCK_SIZE;                                                   // the optimized rule never adapts
     } else if (kind == mcf::PK_BLOCK || kind == mcf::PK_BLOCK_CACHED) {
@@ -726,6 +744,12 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->metrics.h2d_time_us = us_since(t_h2d);
 
+    if (cand_cap > 0) {
+        CUDA_TRY(h, h->d_cand.ensure(2 * (size_t)cand_cap)); CUDA_TRY(h, h->d_cand_scratch.ensure(2 * (size_t)cand_cap));
+        CUDA_TRY(h, h->d_cand_cost.ensure(2 * (size_t)cand_cap));
+        P.cand = h->d_cand.p; P.cand_scratch = h->d_cand_scratch.p; P.cand_cost = h->d_cand_cost.p; P.cand_cap = cand_cap;
+        P.list_length = list_length; P.minor_limit = minor_limit; P.head_length = head_length;
+    }
     P.rc_cache = kind == mcf::PK_BLOCK_CACHED ? h->d_rc.p : nullptr;
     P.kind = kind; P.block_size = block > 0 ? block : 1; P.dyn_min_block = dyn_min; P.max_block_size = cfg.max_block_size;
     P.adaptive = (cfg.flags & MCF_FLAG_ADAPTIVE_BLOCK_SIZE) ? 1 : 0; P.consecutive = cfg.consecutive_hits_before_adapt;
@@ -761,7 +785,8 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     h->metrics.d2h_bytes = (int64_t)m * 8 + (int64_t)n * 8 + (int64_t)sizeof(ctl);
 
     mcf_metrics& M = h->metrics;
-    M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = (kind >= 2) ? ctl.final_block_size : 0;
+    M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked;
+    M.final_block_size = (kind >= 2 && kind != mcf::PK_CAND_LIST && kind != mcf::PK_ALT_LIST) ? ctl.final_block_size : 0;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
     M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
     M.pivot_search_time_us = ctl.ns_price / 1000.0; M.cycle_time_us = ctl.ns_cycle / 1000.0; M.tree_update_time_us = ctl.ns_update / 1000.0;

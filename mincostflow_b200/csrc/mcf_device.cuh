@@ -31,8 +31,10 @@ enum : int {
 };
 
 // pricing kinds (PivotRule.cs:7-40; 3 = CachedBlockSearchPivot, NS.cs:1445-1599; 4 = BlockSearchPivotOptimized,
-// Internal/BlockSearchPivotOptimized.cs:39-157)
-enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3, PK_BLOCK_OPT = 4 };
+// Internal/BlockSearchPivotOptimized.cs:39-157; 5 / 6 = the Candidate List / Altering List rules PivotRule.cs:33-40 declares and
+// NS.cs:884 throws on, defined as LEMON's network_simplex.h:413-518 / :521-635)
+enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3, PK_BLOCK_OPT = 4, PK_CAND_LIST = 5, PK_ALT_LIST = 6 };
+constexpr int kSortCap = 4096;          // Altering List: entries sorted per pass in shared memory (16 B each, in the cycle-list staging area)
 
 struct __align__(16) PriceRec {         // one pricing candidate (per CTA, per round)
     long long c;                        // reduced cost (negative when valid, 0 = none)
@@ -86,6 +88,13 @@ struct Params {
     PriceRec* part;                     // [2][gridDim.x]
     CycEnt* list; int list_cap;
     int* stem_scratch;                  // [6][n+1] flat engine: stems longer than kStemCap are ranked and read here
+    // Candidate List / Altering List rules: the list (double buffered), reduced costs / scratch of the list pass (CTA 0 only)
+    int* cand;                          // [2][cand_cap]
+    long long* cand_cost;               // [2][cand_cap]
+    int* cand_scratch;                  // [2][cand_cap]
+    int cand_cap;
+    int list_length, minor_limit;       // Candidate List (network_simplex.h:441-458)
+    int head_length;                    // Altering List (:563-580); its block size is block_size
     Ctl* ctl;
     // pricing configuration (BlockSearchPivot ctor, NS.cs:1304-1337; adaptive rule :1399-1438)
     int kind;

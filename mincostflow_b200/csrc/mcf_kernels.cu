@@ -81,6 +81,9 @@ struct Shared {
     Key red[2][kWarps];
     PriceRec rec;                      // winning pricing candidate of this pivot
     int found, abort, nstem;
+    int wsum[kWarps];                  // list rules: per-warp counts of a block-wide prefix
+    int cl_base, cl_total, cl_bo;      // list rules: results of the reductions over the CTAs' records
+    long long cl_bc;
     int h_inF, h_inS;                  // in[first], in[second]
     long long h_piF, h_piS, h_up, h_fl;
     int st_u[kStemCap], st_in[kStemCap], st_z[kStemCap], st_pd[kStemCap];   // stem s_0 = u_in .. s_m = u_out
@@ -129,8 +132,7 @@ __device__ __forceinline__ void publish_candidate(const Params& P, int buf, long
 }
 
 // Best Eligible inner loop (NS.cs:1649-1658) over quads of arcs: 128-bit loads of source / target / cost / state, the
-// two potential gathers, strict '<' in ascending arc order.  Software-pipelined: the next quad's arc data is in flight
-// while the current quad's potentials are gathered (the loop is latency-, not bandwidth-bound otherwise).
+// two potential gathers, strict '<' in ascending arc order.
 struct ArcQuad { int4 s, t, c, st; };
 __device__ __forceinline__ ArcQuad load_quad(const Params& P, int q)
 {
@@ -161,16 +163,13 @@ __device__ __forceinline__ void price_quad(const Params& P, const ArcQuad& a, in
 }
 __device__ __forceinline__ void sweep_quads(const Params& P, int first, int stride, int nquad, Key& best)
 {
-    int q = first;
-    if (q >= nquad) return;
-    ArcQuad cur = load_quad(P, q);
-    for (;;) {
-        const int qn = q + stride;
-        ArcQuad nxt = cur;
-        if (qn < nquad) nxt = load_quad(P, qn);
-        price_quad(P, cur, q, best);
-        if (qn >= nquad) break;
-        cur = nxt; q = qn;
+    // No software pipelining: with 1 024 threads per SM the other warps cover the latency, and the shorter live ranges
+    // (48 registers instead of 64) measured 4 % faster (tools/micro/sweep.cu, profiles/r02_micro_sweep.txt: every launch
+    // shape / unroll / cache-hint variant ends between 46 and 49 us at 2^20 - the L1TEX wavefront rate of the random
+    // pi[target] gather, one 128-byte line per arc, is the bound).
+    for (int q = first; q < nquad; q += stride) {
+        const ArcQuad a = load_quad(P, q);
+        price_quad(P, a, q, best);
     }
 }
 
@@ -247,6 +246,125 @@ __device__ __forceinline__ OptPiece opt_piece(long long p, int S, int B, int L1)
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------ list rules
+// Candidate List / Altering List (PivotRule.cs:33-40; the C# port throws at NS.cs:884, LEMON implements them at
+// network_simplex.h:413-518 and :521-635 - that is the definition followed here, on the port's arrays and arc order).
+
+static_assert(kWarps == 32, "block_excl_count scans the warp totals in one warp");
+// Exclusive count of `f` over the threads of the CTA in thread order; `total` = the CTA-wide count.  Called by all threads.
+__device__ __forceinline__ int block_excl_count(bool f, int* s_w, int& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    const int w = s_w[lane];
+    int incl = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    const int before = __shfl_sync(0xffffffffu, incl - w, warp);
+    __syncthreads();
+    return before + __popc(m & ((1u << lane) - 1u));
+}
+
+// thread 0: the entering arc's record as phase B reads it
+__device__ __forceinline__ void fill_rec(const Params& P, Shared& sh, long long c, int arc, int off)
+{
+    sh.rec.c = c; sh.rec.arc = arc; sh.rec.off = off;
+    sh.rec.src = __ldg(P.src + arc); sh.rec.tgt = __ldg(P.tgt + arc); sh.rec.cost = __ldg(P.cost + arc); sh.rec.state = __ldcg(P.state + arc);
+}
+
+// The pass both list rules start with (network_simplex.h:467-479, :587-596): an entry that is no longer eligible is replaced by
+// the last entry of the list, which is examined in its place.  In closed form, with K entries still eligible: those at positions
+// < K stay where they are, and the holes among the first K positions receive, in ascending order, the eligible entries of the
+// tail [K, L) in DESCENDING position order.  dst[0, K) = the list after the pass, P.cand_cost[0, K) = the reduced costs in that
+// order (which is also the order LEMON examines them in).  One CTA, all threads; returns K.
+__device__ int recheck_list(const Params& P, Shared& sh, const int* src, int L, int* dst)
+{
+    long long* const cc = P.cand_cost; long long* const tail_c = P.cand_cost + P.cand_cap;
+    int* const holes = P.cand_scratch; int* const tail_arc = P.cand_scratch + P.cand_cap;
+    const int tid = threadIdx.x;
+    int K = 0;
+    for (int base = 0; base < L; base += kThreads) {
+        const int i = base + tid;
+        bool keep = false;
+        if (i < L) { const long long c = reduced_cost(P, __ldcg(src + i)); cc[i] = c; keep = c < 0; }
+        K += __syncthreads_count(keep);
+    }
+    int run = 0, nh = 0;
+    for (int base = 0; base < L; base += kThreads) {
+        const int i = base + tid;
+        long long c = 0; int e = 0; bool keep = false;
+        if (i < L) { c = cc[i]; e = __ldcg(src + i); keep = c < 0; }
+        int tot;
+        const int pre = run + block_excl_count(keep, sh.wsum, tot);
+        run += tot;
+        nh += __syncthreads_count(i < K && !keep);
+        if (i < L) {
+            if (i < K) { if (keep) dst[i] = e; else holes[i - pre] = i; }
+            else if (keep) { const int r = K - pre - 1; tail_arc[r] = e; tail_c[r] = c; }
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < nh; r += kThreads) { const int p = __ldcg(holes + r); dst[p] = __ldcg(tail_arc + r); cc[p] = __ldcg(tail_c + r); }
+    __syncthreads();
+    return K;
+}
+
+// Altering List, "extend the list" (network_simplex.h:602-625) over the scan offsets [lo, hi): eligible arcs are appended in scan
+// order behind the `curr` entries dst / P.cand_cost hold.  One CTA, all threads; returns the new length.
+__device__ int append_block(const Params& P, Shared& sh, int next_arc, long long lo, long long hi, int* dst, int curr)
+{
+    long long* const cc = P.cand_cost;
+    for (long long base = lo; base < hi; base += kThreads) {
+        const long long off = base + threadIdx.x;
+        bool e = false; long long c = 0; int idx = 0;
+        if (off < hi) { idx = next_arc + (int)off; if (idx >= P.S) idx -= P.S; c = reduced_cost(P, idx); e = c < 0; }
+        int tot;
+        const int r = block_excl_count(e, sh.wsum, tot);
+        if (e) { dst[curr + r] = idx; cc[curr + r] = c; }
+        curr += tot;
+    }
+    __syncthreads();
+    return curr;
+}
+
+// Altering List, the partial sort and the selection (network_simplex.h:621-632): the new_length = min(head + 1, curr) cheapest
+// entries ascending by (reduced cost, position in the list) - std::partial_sort leaves the order of equal costs open; position
+// order is the one this engine and its oracle define - then the first becomes the entering arc and the last takes its place.
+// Bitonic sort in shared memory, kSortCap entries per pass (the running head is carried into the next pass).  One CTA, all threads.
+struct SortKey { long long c; int pos; int arc; };
+__device__ __forceinline__ bool sort_less(const SortKey& x, const SortKey& y) { return x.c < y.c || (x.c == y.c && x.pos < y.pos); }
+__device__ void alt_sort_select(const Params& P, SortKey* sk, int* lst, int curr, long long& win_c, int& win_arc, int& newlen)
+{
+    const int tid = threadIdx.x;
+    const int K = P.head_length + 1 < curr ? P.head_length + 1 : curr;
+    int have = 0, i0 = 0;
+    while (i0 < curr) {
+        const int take = curr - i0 < kSortCap - have ? curr - i0 : kSortCap - have;
+        for (int t = tid; t < take; t += kThreads) { SortKey k; k.c = __ldcg(P.cand_cost + i0 + t); k.pos = i0 + t; k.arc = __ldcg(lst + i0 + t); sk[have + t] = k; }
+        const int nn = have + take;
+        int n2 = 32; while (n2 < nn) n2 <<= 1;
+        for (int t = nn + tid; t < n2; t += kThreads) { SortKey k; k.c = LLONG_MAX; k.pos = INT_MAX; k.arc = -1; sk[t] = k; }
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n2 >> 1); t += kThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const bool up = (i & k) == 0;
+                    const SortKey a = sk[i], b = sk[l];
+                    if (sort_less(b, a) == up) { sk[i] = b; sk[l] = a; }
+                }
+                __syncthreads();
+            }
+        have = K < nn ? K : nn; i0 += take;
+    }
+    win_c = sk[0].c; win_arc = sk[0].arc; newlen = K - 1;
+    for (int t = tid; t < K - 1; t += kThreads) lst[t] = t == 0 ? sk[K - 1].arc : sk[t].arc;
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 
 __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
@@ -266,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
     long long max_cycle = 0, max_stem = 0, rounds_total = 0, arcs_priced_opt = 0;
     int price_buf = 0;                 // parity of the pricing round (double-buffers part[])
     int cache_dirty = 1;               // _reducedCostsDirty, NS.cs:65
+    int cl_len = 0, cl_minor = 0, cl_buf = 0;   // list rules: _curr_length, _minor_count, list buffer that holds the current list
     int status = ST_NOT_SOLVED;
     unsigned long long t_price = 0, t_cycle = 0, t_update = 0, t_mark = 0, t_begin = 0;
     if (cta == 0 && tid == 0) t_begin = t_mark = globaltimer_ns();
@@ -485,6 +604,252 @@ __global__ void __launch_bounds__(kThreads, 1) ns_pivot_kernel(const Params P)
             }
             if (status != ST_NOT_SOLVED) break;
             arcs_priced_opt += arcs_this;
+        } else if (P.kind == PK_CAND_LIST) {
+            // CandidateListPivotRule::findEnteringArc, network_simplex.h:461-516
+            bool major = true;
+            if (cl_len > 0 && cl_minor < P.minor_limit) {
+                // minor iteration (:464-482): CTA 0 re-prices the list; the best eligible entry, first in list order among equals
+                cl_minor++;
+                if (cta == 0) {
+                    int* const dst = P.cand + (size_t)(cl_buf ^ 1) * P.cand_cap;
+                    const int K = recheck_list(P, sh, P.cand + (size_t)cl_buf * P.cand_cap, cl_len, dst);
+                    Key kb; kb.a = 0; kb.b = INT_MAX; kb.idx = tid;
+                    for (int p = tid; p < K; p += kThreads) { const long long c = __ldcg(P.cand_cost + p); if (c < kb.a) { kb.a = c; kb.b = p; } }
+                    kb = block_min(kb, sh.red[0]);
+                    if (tid == 0) {
+                        PriceRec r; r.c = K > 0 ? kb.a : 0; r.arc = K > 0 ? __ldcg(dst + kb.b) : -1; r.off = K; r.src = r.tgt = r.cost = r.state = 0;
+                        P.part[(size_t)price_buf * G] = r;
+                    }
+                }
+                arcs_this += cl_len;
+                if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                rounds_total++;
+                if (tid == 0) {
+                    const long long c = __ldcg(&P.part[(size_t)price_buf * G].c);
+                    sh.found = c < 0 ? 1 : 0; sh.cl_total = __ldcg(&P.part[(size_t)price_buf * G].off);
+                    if (c < 0) fill_rec(P, sh, c, __ldcg(&P.part[(size_t)price_buf * G].arc), 0);
+                }
+                __syncthreads();
+                price_buf ^= 1; cl_buf ^= 1;
+                if (sh.found) { cl_len = sh.cl_total; found = true; major = false; }
+                __syncthreads();
+            }
+            if (major) {
+                // major iteration (:485-514): the first list_length eligible arcs of the cyclic scan from next_arc; windows of
+                // G x rows x 1024 arcs per round, every CTA a contiguous part of the window, ranks by prefix over the CTAs
+                const int LL = P.list_length;
+                int* const wl = P.cand + (size_t)cl_buf * P.cand_cap;
+                int curr = 0, bestoff = 0, rows = 1, new_next = next_arc;
+                long long bestc = 0, done = 0;
+                for (;;) {
+                    const long long lo = done + (long long)cta * rows * kThreads;
+                    bool el[4]; long long cs[4]; int rk[4];
+                    int cnt = 0;
+                    Key kb; kb.a = 0; kb.b = INT_MAX; kb.idx = tid;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        el[k] = false; cs[k] = 0; rk[k] = 0;
+                        if (k < rows) {
+                            const long long off = lo + (long long)k * kThreads + tid;
+                            bool e = false; long long c = 0;
+                            if (off < S) { int idx = next_arc + (int)off; if (idx >= S) idx -= S; c = reduced_cost(P, idx); e = c < 0; }
+                            int tot;
+                            const int r = block_excl_count(e, sh.wsum, tot);
+                            el[k] = e; cs[k] = c; rk[k] = cnt + r; cnt += tot;
+                            if (e && c < kb.a) { kb.a = c; kb.b = (int)off; }
+                        }
+                    }
+                    kb = block_min(kb, sh.red[0]);
+                    if (tid == 0) { PriceRec r; r.c = kb.a; r.off = kb.b; r.arc = cnt; r.src = r.tgt = r.cost = r.state = 0; P.part[(size_t)price_buf * G + cta] = r; }
+                    if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    rounds_total++;
+                    if (warp == 0) {                   // prefix of the CTAs' counts, best (cost, offset) of the round
+                        int carry = 0;
+                        Key kr; kr.a = 0; kr.b = INT_MAX; kr.idx = 0;
+                        for (int j0 = 0; j0 < G; j0 += 32) {
+                            const int j = j0 + lane;
+                            const PriceRec* q = &P.part[(size_t)price_buf * G + (j < G ? j : 0)];
+                            const int cj = j < G ? __ldcg(&q->arc) : 0;
+                            int incl = cj;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                            if (j == cta) sh.cl_base = carry + incl - cj;
+                            carry += __shfl_sync(0xffffffffu, incl, 31);
+                            if (cj > 0) { Key t; t.a = __ldcg(&q->c); t.b = __ldcg(&q->off); t.idx = 0; if (key_less(t, kr)) kr = t; }
+                        }
+                        kr = warp_min(kr);
+                        if (lane == 0) { sh.cl_total = carry; sh.cl_bc = kr.a; sh.cl_bo = kr.b; }
+                    }
+                    __syncthreads();
+                    price_buf ^= 1;
+                    const int T = sh.cl_total, base = curr + sh.cl_base;
+                    const bool cross = curr + T >= LL;          // the list is full inside this window (:493, :503)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (el[k] && base + rk[k] < LL) {
+                            int idx = next_arc + (int)(lo + (long long)k * kThreads + tid); if (idx >= S) idx -= S;
+                            wl[base + rk[k]] = idx;
+                        }
+                    if (!cross) {
+                        if (T > 0 && sh.cl_bc < bestc) { bestc = sh.cl_bc; bestoff = sh.cl_bo; }
+                        curr += T;
+                        __syncthreads();
+                    } else {
+                        // only the arcs up to the one that filled the list were examined: best among those, and where the scan stopped
+                        Key kr; kr.a = 0; kr.b = INT_MAX; kr.idx = tid;
+                        int fo = -1;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (el[k] && base + rk[k] < LL) {
+                                const int off = (int)(lo + (long long)k * kThreads + tid);
+                                if (cs[k] < kr.a) { kr.a = cs[k]; kr.b = off; }
+                                if (base + rk[k] == LL - 1) fo = off;
+                            }
+                        if (tid == 0) sh.found = -1;
+                        kr = block_min(kr, sh.red[0]);
+                        if (fo >= 0) sh.found = fo;                   // at most one thread of the grid holds the entry that filled the list
+                        __syncthreads();
+                        const int fo_cta = sh.found;
+                        if (tid == 0) { PriceRec r; r.c = kr.a; r.off = kr.b; r.arc = fo_cta; r.src = r.tgt = r.cost = r.state = 0; P.part[(size_t)price_buf * G + cta] = r; }
+                        if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                        rounds_total++;
+                        if (warp == 0) {
+                            Key kq; kq.a = 0; kq.b = INT_MAX; kq.idx = 0;
+                            int fmax = -1;
+                            for (int j = lane; j < G; j += 32) {
+                                const PriceRec* q = &P.part[(size_t)price_buf * G + j];
+                                Key t; t.a = __ldcg(&q->c); t.b = __ldcg(&q->off); t.idx = 0;
+                                if (t.a < 0 && key_less(t, kq)) kq = t;
+                                const int f = __ldcg(&q->arc); if (f > fmax) fmax = f;
+                            }
+                            kq = warp_min(kq);
+                            fmax = __reduce_max_sync(0xffffffffu, fmax);
+                            if (lane == 0) { sh.cl_bc = kq.a; sh.cl_bo = kq.b; sh.cl_total = fmax; }
+                        }
+                        __syncthreads();
+                        price_buf ^= 1;
+                        if (sh.cl_bc < bestc) { bestc = sh.cl_bc; bestoff = sh.cl_bo; }
+                        const int fill_off = sh.cl_total;
+                        curr = LL;
+                        arcs_this += fill_off + 1;
+                        new_next = next_arc + fill_off; if (new_next >= S) new_next -= S;          // `_next_arc = e` (:512), e = the arc that filled the list
+                        __syncthreads();
+                        break;
+                    }
+                    done += (long long)G * rows * kThreads;
+                    if (done >= S) { arcs_this += S; break; }                                     // both loops ran out: e == _next_arc
+                    rows = rows * 2 < 4 ? rows * 2 : 4;
+                }
+                if (status != ST_NOT_SOLVED) break;
+                if (curr > 0) {
+                    if (tid == 0) { int idx = next_arc + bestoff; if (idx >= S) idx -= S; fill_rec(P, sh, bestc, idx, bestoff); }
+                    __syncthreads();
+                    found = true; cl_minor = 1; next_arc = new_next;
+                }
+                cl_len = curr;
+            }
+            arcs_checked += arcs_this;
+        } else if (P.kind == PK_ALT_LIST) {
+            // AlteringListPivotRule::findEnteringArc, network_simplex.h:583-633.  CTA 0 keeps the list: it re-prices it, extends it
+            // by the first block of the scan (and the second when the first left it at or below the head length), sorts and selects.
+            // Only when the list is empty after the first block does the rest of the search go over the grid: the first block with an
+            // eligible arc is found by all CTAs, CTA 0 then extends the list by that block.
+            // Record in part[buf][0]: c / arc = entering arc, off = new list length, src = blocks examined, tgt = bit 0 decided, bit 1 scan exhausted
+            const int H = P.head_length;
+            int* const src_l = P.cand + (size_t)cl_buf * P.cand_cap;
+            int* const dst_l = P.cand + (size_t)(cl_buf ^ 1) * P.cand_cap;
+            SortKey* const sk = reinterpret_cast<SortKey*>(dyn_smem);
+            auto finish = [&](int curr, int blocks, bool exhausted) {          // CTA 0: sort, select, publish
+                long long wc = 0; int wa = -1, nl = 0;
+                if (curr > 0) alt_sort_select(P, sk, dst_l, curr, wc, wa, nl);
+                if (tid == 0) { PriceRec r; r.c = wc; r.arc = wa; r.off = nl; r.src = blocks; r.tgt = 1 | (exhausted ? 2 : 0); r.cost = r.state = 0; P.part[(size_t)price_buf * G] = r; }
+            };
+            const long long nblk = ((long long)S + B - 1) / B;
+            if (cta == 0) {
+                int curr = recheck_list(P, sh, src_l, cl_len, dst_l);
+                int b = 0; bool stop = false, exhausted = false;
+                for (;;) {
+                    const long long lo = (long long)b * B;
+                    if (lo >= S) { exhausted = true; break; }
+                    long long hi = lo + B; if (hi > S) hi = S;
+                    curr = append_block(P, sh, next_arc, lo, hi, dst_l, curr);
+                    ++b;
+                    if (hi - lo < B) { exhausted = true; break; }              // the scan ran out inside a block: `--cnt == 0` never fired
+                    if (curr > (b == 1 ? H : 0)) { stop = true; break; }       // :608-612 / :619-623
+                    if (curr == 0) break;
+                }
+                if (stop || exhausted) finish(curr, b, exhausted);
+                else if (tid == 0) { PriceRec r; r.c = 0; r.arc = -1; r.off = 0; r.src = b; r.tgt = 0; r.cost = r.state = 0; P.part[(size_t)price_buf * G] = r; }
+            }
+            arcs_this = cl_len;
+            if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            rounds_total++;
+            int4 r0 = __ldcg(reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G])), r1 = __ldcg(reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G]) + 1);
+            price_buf ^= 1;
+            int blocks = r0.w;                          // PriceRec: {c (x, y), arc (z), src (w)}, {tgt (x), cost (y), state (z), off (w)}
+            if (!(r1.x & 1)) {
+                // the list is empty after `blocks` blocks: first later block with an eligible arc
+                long long b0 = blocks;
+                int L = P.lookahead0;
+                long long hit = -1;
+                while (b0 < nblk) {
+                    const int nact = L < G ? L : G;
+                    int any = 0;
+                    if (cta < nact && b0 + cta < nblk) {
+                        const long long lo = (b0 + cta) * B; long long hi = lo + B; if (hi > S) hi = S;
+                        for (long long off = lo + tid; off < hi; off += kThreads) {
+                            int idx = next_arc + (int)off; if (idx >= S) idx -= S;
+                            if (reduced_cost(P, idx) < 0) { any = 1; break; }
+                        }
+                    }
+                    any = __syncthreads_or(any);
+                    if (tid == 0 && cta < nact) P.part[(size_t)price_buf * G + cta].c = any ? -1 : 0;
+                    if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    rounds_total++;
+                    if (warp == 0) {
+                        int win = -1;
+                        for (int j0 = 0; j0 < nact && win < 0; j0 += 32) {
+                            const int j = j0 + lane;
+                            const long long c = j < nact ? __ldcg(&P.part[(size_t)price_buf * G + j].c) : 0;
+                            const unsigned mask = __ballot_sync(0xffffffffu, c < 0);
+                            if (mask) win = j0 + __ffs(mask) - 1;
+                        }
+                        if (lane == 0) sh.found = win;
+                    }
+                    __syncthreads();
+                    price_buf ^= 1;
+                    const int win = sh.found;
+                    __syncthreads();
+                    if (win >= 0) { hit = b0 + win; break; }
+                    b0 += nact;
+                    L = L * 2 < G ? L * 2 : G;
+                }
+                if (status != ST_NOT_SOLVED) break;
+                if (hit < 0) { r0.x = r0.y = 0; r1.x = 3; blocks = (int)nblk; }            // nothing eligible anywhere: optimal
+                else {
+                    if (cta == 0) {
+                        const long long lo = hit * B; long long hi = lo + B; if (hi > S) hi = S;
+                        const int curr = append_block(P, sh, next_arc, lo, hi, dst_l, 0);
+                        finish(curr, (int)hit + 1, hi - lo < B);
+                    }
+                    if (!grid_barrier(P, sh, bar_target)) { status = ST_ERR_BARRIER_TIMEOUT; break; }
+                    rounds_total++;
+                    r0 = __ldcg(reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G])); r1 = __ldcg(reinterpret_cast<const int4*>(&P.part[(size_t)price_buf * G]) + 1);
+                    price_buf ^= 1;
+                    blocks = r0.w;
+                }
+            }
+            const long long wc = (long long)(((unsigned long long)(unsigned)r0.y << 32) | (unsigned)r0.x);
+            const bool exhausted = (r1.x & 2) != 0;
+            arcs_this += exhausted ? S : (int)((long long)blocks * B);
+            cl_buf ^= 1;
+            if (wc < 0) {
+                if (tid == 0) fill_rec(P, sh, wc, r0.z, 0);
+                __syncthreads();
+                found = true; cl_len = r1.w;
+                if (!exhausted) { int e = next_arc + (int)((long long)blocks * B) - 1; if (e >= S) e -= S; next_arc = e; }       // `_next_arc = e` (:630), the last arc examined
+            } else cl_len = 0;
+            arcs_checked += arcs_this;
         } else {  // PK_BEST: coalesced 128-bit sweep over all S arcs, lowest arc id wins ties (NS.cs:1649-1658)
             const int r = grid_best_in_range(P, sh, 0, S, 0, price_buf, bar_target);
             if (r < 0) { status = ST_ERR_BARRIER_TIMEOUT; break; }

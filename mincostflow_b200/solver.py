@@ -376,8 +376,10 @@ class NetworkSimplex:
         self._check(self._lib.mcf_set_options(self._h, C.byref(self._opt)))
 
     def Solve(self) -> SolverStatus:
-        if int(self._opt.pivot_rule) > int(PivotRule.BlockSearch):
-            raise NotImplementedError(f"Pivot rule {PivotRule(self._opt.pivot_rule).name} not implemented yet")   # NetworkSimplex.cs:884
+        # CandidateList / AlteringList: the reference throws (NetworkSimplex.cs:884); here they run, defined as LEMON's
+        # (network_simplex.h:413-635).  The optimized wrapper still knows only the first three rules (NetworkSimplex.cs:1689-1695).
+        if int(self._opt.pivot_rule) > int(PivotRule.BlockSearch) and int(self._opt.optimized_pivot):
+            raise NotImplementedError(f"Optimized pivot rule {PivotRule(self._opt.pivot_rule).name} not implemented")
         self._push()
         st = C.c_int32(0)
         self._flows = self._pots = None

@@ -40,7 +40,8 @@ extern "C" int lemon_ns_solve(int n, int m, const int32_t* src, const int32_t* t
     NS ns(g);
     ns.lowerMap(lo).upperMap(up).costMap(co).supplyMap(su);
     ns.supplyType(supply_type == 0 ? NS::GEQ : NS::LEQ);
-    NS::PivotRule rule = pivot_rule == 0 ? NS::FIRST_ELIGIBLE : pivot_rule == 1 ? NS::BEST_ELIGIBLE : NS::BLOCK_SEARCH;
+    NS::PivotRule rule = pivot_rule == 0 ? NS::FIRST_ELIGIBLE : pivot_rule == 1 ? NS::BEST_ELIGIBLE : pivot_rule == 3 ? NS::CANDIDATE_LIST
+                       : pivot_rule == 4 ? NS::ALTERING_LIST : NS::BLOCK_SEARCH;       // PivotRule.cs:7-40 values
     auto t0 = std::chrono::steady_clock::now();
     NS::ProblemType st = ns.run(rule);
     auto t1 = std::chrono::steady_clock::now();

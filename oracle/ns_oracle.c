@@ -54,6 +54,10 @@ typedef struct {
     /* pivot rule state */
     int block_size, next_arc, consecutive_low, consecutive_high, dyn_min_block;
     int64_t arcs_checked_pivot;
+    /* Candidate List / Altering List rules (LEMON network_simplex.h:415-635; the C# port declares them, PivotRule.cs:33-40,
+     * and throws NotImplementedException, NS.cs:884) */
+    int *candidates; int64_t *cand_cost;
+    int list_length, minor_limit, curr_length, minor_count, head_length, alt_block;
     ns_oracle_result *res;
     const ns_oracle_options *opt;
 } ns_t;
@@ -360,6 +364,116 @@ static int find_best(ns_t *s)
     return 0;
 }
 
+/* CandidateListPivotRule, lemon-1.3.1/lemon/network_simplex.h:413-518 (constructor :441-458, findEnteringArc :461-516),
+ * on the C# port's arrays and arc order (the port has no implementation: NS.cs:884 throws). */
+static void candidate_ctor(ns_t *s)
+{
+    int l = (int)(0.25 * sqrt((double)s->search_arc_num));
+    s->list_length = l > 10 ? l : 10;
+    int ml = (int)(0.1 * s->list_length);
+    s->minor_limit = ml > 3 ? ml : 3;
+    s->curr_length = s->minor_count = 0; s->next_arc = 0;
+    s->candidates = (int *)calloc((size_t)s->list_length, 4);
+}
+
+static int find_candidate_list(ns_t *s)
+{
+    int64_t min, c; int e; const int S = s->search_arc_num;
+    if (s->curr_length > 0 && s->minor_count < s->minor_limit) {
+        /* minor iteration: best eligible arc of the list; arcs that are no longer eligible are replaced by the last entry */
+        s->minor_count++;
+        min = 0;
+        for (int i = 0; i < s->curr_length; ++i) {
+            e = s->candidates[i];
+            c = red_cost(s, e);
+            s->arcs_checked_pivot++;
+            if (c < min) { min = c; s->in_arc = e; }
+            else if (c >= 0) s->candidates[i--] = s->candidates[--s->curr_length];
+        }
+        if (min < 0) return 1;
+    }
+    /* major iteration: a new list from the cyclic scan */
+    min = 0; s->curr_length = 0;
+    for (e = s->next_arc; e != S; ++e) {
+        c = red_cost(s, e); s->arcs_checked_pivot++;
+        if (c < 0) {
+            s->candidates[s->curr_length++] = e;
+            if (c < min) { min = c; s->in_arc = e; }
+            if (s->curr_length == s->list_length) goto search_end;
+        }
+    }
+    for (e = 0; e != s->next_arc; ++e) {
+        c = red_cost(s, e); s->arcs_checked_pivot++;
+        if (c < 0) {
+            s->candidates[s->curr_length++] = e;
+            if (c < min) { min = c; s->in_arc = e; }
+            if (s->curr_length == s->list_length) goto search_end;
+        }
+    }
+    if (s->curr_length == 0) return 0;
+search_end:
+    s->minor_count = 1;
+    s->next_arc = e;
+    return 1;
+}
+
+/* AlteringListPivotRule, network_simplex.h:521-635 (constructor :563-580, findEnteringArc :583-633).  std::partial_sort
+ * leaves the order of entries with equal cost unspecified; this restatement - and the GPU engine with it - orders ties
+ * by their position in the list when the sort starts (a stable partial sort, one of the orders the standard allows). */
+static void altering_ctor(ns_t *s)
+{
+    int b = (int)(1.0 * sqrt((double)s->search_arc_num));
+    s->alt_block = b > 10 ? b : 10;
+    int h = (int)(0.01 * s->alt_block);
+    s->head_length = h > 3 ? h : 3;
+    s->candidates = (int *)calloc((size_t)s->head_length + s->alt_block, 4);
+    s->cand_cost = (int64_t *)calloc((size_t)s->search_arc_num + 1, 8);
+    s->curr_length = 0; s->next_arc = 0;
+}
+
+static int find_altering_list(ns_t *s)
+{
+    int e; int64_t c; const int S = s->search_arc_num;
+    for (int i = 0; i != s->curr_length; ++i) {          /* check the current list */
+        e = s->candidates[i];
+        c = red_cost(s, e); s->arcs_checked_pivot++;
+        if (c < 0) s->cand_cost[e] = c;
+        else s->candidates[i--] = s->candidates[--s->curr_length];
+    }
+    int cnt = s->alt_block, limit = s->head_length;      /* extend it */
+    for (e = s->next_arc; e != S; ++e) {
+        c = red_cost(s, e); s->arcs_checked_pivot++;
+        if (c < 0) { s->cand_cost[e] = c; s->candidates[s->curr_length++] = e; }
+        if (--cnt == 0) { if (s->curr_length > limit) goto search_end; limit = 0; cnt = s->alt_block; }
+    }
+    for (e = 0; e != s->next_arc; ++e) {
+        c = red_cost(s, e); s->arcs_checked_pivot++;
+        if (c < 0) { s->cand_cost[e] = c; s->candidates[s->curr_length++] = e; }
+        if (--cnt == 0) { if (s->curr_length > limit) goto search_end; limit = 0; cnt = s->alt_block; }
+    }
+    if (s->curr_length == 0) return 0;
+search_end:;
+    /* partial sort: the new_length cheapest entries in front, ascending by (cost, position before the sort) */
+    int new_length = s->head_length + 1 < s->curr_length ? s->head_length + 1 : s->curr_length;
+    int *top = (int *)malloc((size_t)new_length * 4);     /* positions, kept sorted */
+    int nt = 0;
+    for (int i = 0; i < s->curr_length; ++i) {
+        const int64_t ci = s->cand_cost[s->candidates[i]];
+        if (nt == new_length && !(ci < s->cand_cost[s->candidates[top[nt - 1]]])) continue;
+        int j = nt < new_length ? nt++ : nt - 1;
+        while (j > 0 && ci < s->cand_cost[s->candidates[top[j - 1]]]) { top[j] = top[j - 1]; --j; }
+        top[j] = i;
+    }
+    for (int j = 0; j < nt; ++j) top[j] = s->candidates[top[j]];
+    memcpy(s->candidates, top, (size_t)nt * 4);
+    free(top);
+    s->in_arc = s->candidates[0];
+    s->next_arc = e;
+    s->candidates[0] = s->candidates[new_length - 1];
+    s->curr_length = new_length - 1;
+    return 1;
+}
+
 /* Internal/BlockSearchPivotOptimized.cs:39-157.  ProcessArcRange falls through into its scalar loop
  * after ProcessArcRangeSIMD returns early (:74-80): cnt is then 0, `--cnt == 0` cannot fire again, and the
  * rest of the range is scanned to its end.  opt->simd_width (Vector<long>.Count; 4 on AVX2, 0 = not
@@ -593,7 +707,9 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
     } else {
         int use_cache = (s->cfg.flags & NS_FLAG_REDUCED_COST_CACHING) != 0;
         kind = opt->pivot_rule == NS_PIVOT_BLOCK_SEARCH ? (use_cache ? 3 : 2) : opt->pivot_rule;
-        if (opt->pivot_rule == NS_PIVOT_BLOCK_SEARCH) block_ctor(s); else s->next_arc = 0;
+        if (opt->pivot_rule == NS_PIVOT_CANDIDATE_LIST) { kind = 4; candidate_ctor(s); }
+        else if (opt->pivot_rule == NS_PIVOT_ALTERING_LIST) { kind = 5; altering_ctor(s); }
+        else if (opt->pivot_rule == NS_PIVOT_BLOCK_SEARCH) block_ctor(s); else s->next_arc = 0;
     }
     res->pivot_kind = kind;
     if (kind == 2 || kind == 3) res->initial_block_size = s->block_size;
@@ -620,6 +736,8 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
             case 1: found = find_best(s); break;
             case 2: found = find_block(s, 0); break;
             case 3: found = find_cached(s); break;
+            case 4: found = find_candidate_list(s); break;
+            case 5: found = find_altering_list(s); break;
             case 10: found = find_first_optimized(s); break;
             case 11: found = find_best_optimized(s); break;
             default: found = find_block_optimized(s); break;
@@ -676,7 +794,7 @@ done:
     free(s->lower); free(s->upper); free(s->cost); free(s->flow); free(s->supply); free(s->pi); free(s->orig_lower);
     free(s->source); free(s->target); free(s->state); free(s->parent); free(s->pred); free(s->thread);
     free(s->rev_thread); free(s->succ_num); free(s->last_succ); free(s->pred_dir); free(s->dirty_revs);
-    free(s->reduced_costs);
+    free(s->reduced_costs); free(s->candidates); free(s->cand_cost);
     return 0;
 }
 

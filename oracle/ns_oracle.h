@@ -11,7 +11,7 @@
 extern "C" {
 #endif
 
-enum { NS_PIVOT_FIRST_ELIGIBLE = 0, NS_PIVOT_BEST_ELIGIBLE = 1, NS_PIVOT_BLOCK_SEARCH = 2 };
+enum { NS_PIVOT_FIRST_ELIGIBLE = 0, NS_PIVOT_BEST_ELIGIBLE = 1, NS_PIVOT_BLOCK_SEARCH = 2, NS_PIVOT_CANDIDATE_LIST = 3, NS_PIVOT_ALTERING_LIST = 4 };
 enum { NS_STATUS_NOT_SOLVED = 0, NS_STATUS_OPTIMAL = 1, NS_STATUS_INFEASIBLE = 2, NS_STATUS_UNBOUNDED = 3, NS_STATUS_UNBALANCED = 4 };
 enum { NS_SUPPLY_GEQ = 0, NS_SUPPLY_LEQ = 1 };
 enum {

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-FIRST_ELIGIBLE, BEST_ELIGIBLE, BLOCK_SEARCH = 0, 1, 2
+FIRST_ELIGIBLE, BEST_ELIGIBLE, BLOCK_SEARCH, CANDIDATE_LIST, ALTERING_LIST = 0, 1, 2, 3, 4
 NOT_SOLVED, OPTIMAL, INFEASIBLE, UNBOUNDED, UNBALANCED = 0, 1, 2, 3, 4
 GEQ, LEQ = 0, 1
 FLAG_ADAPTIVE, FLAG_SMALL_BLOCKS, FLAG_CACHING, FLAG_CANDIDATE, FLAG_HOTCOLD, FLAG_EARLY = 1, 2, 4, 8, 16, 32

@@ -155,7 +155,13 @@ static void ErrorBehaviour()
     CHECK_THROWS(solver.GetTotalCost(), InvalidOperationException);
     CHECK(!solver.Validate().IsValid);
     solver.SetPivotRule(PivotRule::CandidateList);
-    CHECK_THROWS(solver.Solve(), NotImplementedException);                        // :884
+    solver.EnableOptimizedPivot(true);
+    CHECK_THROWS(solver.Solve(), NotImplementedException);                        // :1694 (without the optimized wrapper the rule runs, defined as LEMON's)
+    solver.EnableOptimizedPivot(false);
+    solver.SetArcBounds(Arc(0), 0, 10);
+    CHECK(solver.Solve() == SolverStatus::Optimal && solver.GetTotalCost() == 28);
+    solver.SetPivotRule(PivotRule::AlteringList);
+    CHECK(solver.Solve() == SolverStatus::Optimal && solver.GetTotalCost() == 28);
 }
 
 static void DimacsPath(const std::string& dir)

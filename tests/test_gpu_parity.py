@@ -49,6 +49,8 @@ def check_parity(p, rule=mcf.PivotRule.BlockSearch, cfg=None, supply_type=0, opt
         assert (M.initial_block_size, M.final_block_size) == (r.initial_block_size, r.final_block_size), tag
         assert M.total_arcs_checked == r.total_arcs_checked, tag
         assert M.pricing_kind == r.pivot_kind, tag
+    if rule in (mcf.PivotRule.CandidateList, mcf.PivotRule.AlteringList):
+        assert M.total_arcs_checked == r.total_arcs_checked, (tag, M.total_arcs_checked, r.total_arcs_checked)
     if st == mcf.SolverStatus.Optimal:
         assert ns.GetTotalCost() == r.total_cost, tag
         assert np.array_equal(ns.flows(), rflow), tag
@@ -107,8 +109,8 @@ def test_getters_before_solve_and_bad_ids():
         s.GetFlow(mcf.Arc(1))
     with pytest.raises(mcf.ArgumentException):
         s.GetPotential(mcf.Node(-1))
-    s.SetPivotRule(mcf.PivotRule.CandidateList)
-    with pytest.raises(NotImplementedError):                        # NetworkSimplex.cs:884
+    s.SetPivotRule(mcf.PivotRule.CandidateList); s.EnableOptimizedPivot(True)
+    with pytest.raises(NotImplementedError):                        # NetworkSimplex.cs:1694 (the plain rule runs here: test_list_rules_*)
         s.Solve()
 
 
@@ -379,6 +381,38 @@ def test_deep_tree_every_rule_no_engine_limit():
     check_parity(p, mcf.PivotRule.BlockSearch, cfg=mcf.OptimizationConfig(), optimized=True)
     # (the default Solve() would pick CachedBlockSearchPivot here - sparse, m < 50000 - whose O(m)-per-pivot quirk path of the
     # reference does not finish on this instance within minutes on either side; it is covered on AURV19V6 and the 10k/30k NETGEN)
+
+
+LIST_RULES = [mcf.PivotRule.CandidateList, mcf.PivotRule.AlteringList]
+
+
+@pytest.mark.parametrize("rule", LIST_RULES)
+def test_list_rules_small_fixtures_and_lemon_cases(golden, load_fixture, rule):
+    """Candidate List / Altering List (PivotRule.cs:33-40; thrown on at NS.cs:884, defined as LEMON's network_simplex.h:413-635, SURVEY
+    8f-4): status, pivot count, arcs examined, every flow and potential equal the oracle's on the reference's fixtures and LEMON's cases."""
+    for name, e in golden["fixtures"].items():
+        if e.get("stored") and e["m"] <= 40000:
+            check_parity(load_fixture(name), rule, cfg=mcf.OptimizationConfig(), expect_cost=e.get("objective"))
+    for case in golden["lemon_cases"]:
+        p, stype, status, total = lemon_case_problem(golden, case)
+        balanced_opt = int(p.supply.sum()) == 0 and status == 1
+        check_parity(p, rule, cfg=mcf.OptimizationConfig(), supply_type=stype, expect_cost=total if balanced_opt else None)
+
+
+@pytest.mark.parametrize("rule", LIST_RULES)
+def test_list_rules_netgen_and_deep_trees(rule):
+    """Full solves: NETGEN-8 2^8 .. 2^16 (list refills that wrap around the arc array, searches that run dry), a 96 x 96 time-expanded
+    grid and the 9 000-node deep chain (long cycles and stems)."""
+    for k in (8, 11, 14, 16):
+        check_parity(instances.netgen8(k), rule, cfg=mcf.OptimizationConfig())
+    check_parity(instances.grid_time_expanded(96, 96), rule, cfg=mcf.OptimizationConfig())
+    check_parity(deep_chain(), rule, cfg=mcf.OptimizationConfig())
+
+
+@pytest.mark.parametrize("rule", LIST_RULES)
+def test_list_rules_prefix_at_2_20(rule):
+    """BASELINE config 3's instance: the basis after the first 60 000 pivots equals the oracle's (list length 768, blocks of 3 072)."""
+    check_prefix_parity(instances.netgen8(20), rule, 60000)
 
 
 def test_batch_of_64_instances_of_2_18_nodes():

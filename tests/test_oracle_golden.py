@@ -163,3 +163,47 @@ def test_cost_agreement_with_vendored_lemon(golden, load_fixture):
         assert l["status"] == status, (case[0], l["status"])
         if status == 1:
             assert l["cost"] == total, case[0]
+
+
+@pytest.mark.parametrize("rule", [oracle.CANDIDATE_LIST, oracle.ALTERING_LIST])
+def test_list_rules_reach_the_reference_objectives(golden, load_fixture, rule):
+    """Candidate List / Altering List (PivotRule.cs:33-40 declares them, NetworkSimplex.cs:884 throws; restated from LEMON's
+    network_simplex.h:413-635 on the port's arc order).  No pivot-sequence vector exists for them anywhere in the
+    reference, so the pin is: every stored fixture reaches its .sol objective with a solution the restated SolutionValidator accepts,
+    LEMON's balanced known-answer cases agree, and the vendored LEMON build running the SAME rule returns the same cost."""
+    for name, e in golden["fixtures"].items():
+        if not e.get("stored") or e["m"] > 40000:
+            continue
+        p = load_fixture(name)
+        r, flow, pi, _, _ = oracle.solve(p, pivot_rule=rule, auto_config=False)
+        assert r.status == 1 and r.total_cost == e["objective"], (name, rule, r.status, r.total_cost)
+        assert oracle.validate(p, flow, pi, r.total_cost)[0] == 0, name
+        if oracle.lemon_available() and e["m"] <= 10000:
+            assert oracle.lemon_solve(p, pivot_rule=rule)["cost"] == r.total_cost, name
+    for case in golden["lemon_cases"]:
+        p, stype, status, total = lemon_case_problem(golden, case)
+        r, flow, pi, _, _ = oracle.solve(p, pivot_rule=rule, supply_type=stype, auto_config=False)
+        if int(p.supply.sum()) != 0 or status == 3:
+            continue
+        assert r.status == status, (case[0], rule, r.status)
+        if status == 1:
+            assert r.total_cost == total and oracle.validate(p, flow, pi, r.total_cost, supply_type=stype)[0] == 0, case[0]
+
+
+def test_list_rule_parameters_and_list_mechanics():
+    """The constructor arithmetic of network_simplex.h:441-458 / :563-580 and the two list passes on a hand-made instance: a
+    single-source star where every arc is eligible at the start, so the first major iteration fills the list exactly."""
+    from mincostflow_b200 import instances
+    p = instances.netgen8(12)
+    S = p.m + p.n
+    r3, *_ = oracle.solve(p, pivot_rule=oracle.CANDIDATE_LIST, auto_config=False, max_pivots=1)
+    # first major iteration: scans until list_length = max(int(0.25 sqrt(S)), 10) eligible arcs are found
+    ll = max(int(0.25 * np.sqrt(S)), 10)
+    assert r3.total_arcs_checked >= ll and r3.iterations == 1
+    r4, *_ = oracle.solve(p, pivot_rule=oracle.ALTERING_LIST, auto_config=False, max_pivots=1)
+    assert r4.total_arcs_checked % max(int(np.sqrt(S)), 10) == 0 and r4.iterations == 1          # whole blocks
+    # both rules solve to the Block Search optimum with different pivot counts
+    rb, *_ = oracle.solve(p, auto_config=False)
+    rc, *_ = oracle.solve(p, pivot_rule=oracle.CANDIDATE_LIST, auto_config=False)
+    ra, *_ = oracle.solve(p, pivot_rule=oracle.ALTERING_LIST, auto_config=False)
+    assert rb.total_cost == rc.total_cost == ra.total_cost and len({rb.iterations, rc.iterations, ra.iterations}) == 3
