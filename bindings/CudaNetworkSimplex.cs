@@ -21,7 +21,7 @@ namespace MinCostFlow.Core.Cuda
     [StructLayout(LayoutKind.Sequential)]
     public struct McfOptions
     {
-        public int SupplyType, PivotRule, AutoConfiguration, OptimizedPivot, Device, MaxCtas, LookaheadBlocks, Engine, SimdWidth, Reserved0;
+        public int SupplyType, PivotRule, AutoConfiguration, OptimizedPivot, Device, MaxCtas, LookaheadBlocks, Engine, SimdWidth, WarmStart;
         public long StopAfterPivots;
         public double BarrierTimeoutSeconds;
         public McfOptimizationConfig Config;
@@ -81,6 +81,9 @@ namespace MinCostFlow.Core.Cuda
         public CudaNetworkSimplex SetNodeSupply(Node node, long supply) { if (!_graph.IsValidNode(node)) throw new ArgumentException("Invalid node"); _supply[node.Id] = supply; return this; }
         public CudaNetworkSimplex SetSupplyType(SupplyType type) { _opt.SupplyType = (int)type; return this; }
         public CudaNetworkSimplex SetPivotRule(PivotRule rule) { _opt.PivotRule = (int)rule; return this; }
+        /// <summary>README.md:17-18 roadmap item: a Solve() after SetArcCost edits starts from the previous optimal basis (mcf_options.warm_start).</summary>
+        public void EnableWarmStart(bool enable = true) { _opt.WarmStart = enable ? 1 : 0; }
+
         public void EnableOptimizedPivot(bool enable = true)
         {
             _opt.OptimizedPivot = enable ? 1 : 0;

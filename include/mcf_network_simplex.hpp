@@ -196,6 +196,8 @@ public:
     NetworkSimplex& SetPivotRule(PivotRule rule) { opt_.pivot_rule = (int)rule; return *this; }
     // :532; simdWidth = Vector<long>.Count of the host whose optimized Block Search sequence is to be reproduced (4 = x64 AVX2)
     void EnableOptimizedPivot(bool enable = true, int simdWidth = 4) { opt_.optimized_pivot = enable ? 1 : 0; opt_.simd_width = simdWidth; }
+    // SURVEY.md 8f-3 (README.md:17-18 roadmap): re-Solve() after SetArcCost edits starts from the previous optimal basis (mcf_options.warm_start)
+    void EnableWarmStart(bool enable = true) { opt_.warm_start = enable ? 1 : 0; }
     void EnableOptimizations(int flags) { opt_.config.flags = flags; }                                                  // :549-552
     void SetOptimizationConfig(const OptimizationConfig& c)                                                             // :557-561
     {

@@ -97,7 +97,11 @@ typedef struct mcf_options {
                                        0 = Vector.IsHardwareAccelerated false.  With a non-zero width the reference's scalar loop
                                        resumes after the vector loop's early return with its block counter at 0 and scans the
                                        rest of the range; the engine reproduces exactly that */
-    int32_t reserved0;
+    int32_t warm_start;             /* SURVEY.md 8f-3 (README.md:17-18 "warm start" roadmap item; LEMON re-run semantics network_simplex.h:836-884):
+                                       1 = when the previous mcf_solve on this handle ended Optimal and only arc COSTS changed since (same
+                                       topology, bounds, supplies, supply type), start from that solve's optimal basis - tree, arc states and
+                                       flows kept, potentials recomputed for the new costs - instead of the artificial star basis.  Anything
+                                       else falls back to a cold start; mcf_metrics.warm_started says which one ran.  0 (default) = always cold */
     int64_t stop_after_pivots;      /* >0: stop after this many pivots with Status = NotSolved (bounded samples) */
     double barrier_timeout_s;       /* 0 = default 10 s */
     mcf_optimization_config config; /* SetOptimizationConfig, NetworkSimplex.cs:557-561 (used when auto_configuration == 0) */
@@ -134,7 +138,7 @@ typedef struct mcf_metrics {
     double ns_per_clock;                /* team engine: measured SM clock period */
     double phase_us[16];                /* team engine: sub-phase times (0-7 pricing CTA, 8-15 first owner CTA), see DESIGN.md */
     int32_t wide_flows;                 /* team engine: 1 = tree-arc flows resident as int64, 0 = int32 */
-    int32_t reserved1;
+    int32_t warm_started;               /* 1 = this solve started from the previous optimal basis (mcf_options.warm_start) */
 } mcf_metrics;
 
 typedef struct mcf_handle mcf_handle;

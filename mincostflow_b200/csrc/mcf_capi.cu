@@ -98,7 +98,12 @@ struct mcf_handle {
     DevBuf<unsigned> d_done;
     DevBuf<long long> d_piout;
     std::vector<mcf::NodeRec> h_node;
+    // warm start (mcf_options.warm_start): what identifies the problem the device arrays of the last optimal solve belong to
+    bool warm_valid = false;
+    int warm_supply_type = 0, warm_engine = 0;
+    std::vector<int64_t> warm_upper, warm_supply, warm_lower, cur_upper, cur_supply;   // standard form (after the lower-bound shift) + the shift itself
     // host staging for the initial basis
+    std::vector<int> h_depth;
     std::vector<int> h_src, h_tgt, h_cost, h_state, h_in, h_sz, h_parent, h_pd;
     std::vector<long long> h_flow, h_upper, h_pi;
 };
@@ -281,6 +286,73 @@ void build_initial_basis(mcf_handle* h, int64_t art_cost)
         }
     }
     h->h_in[root] = 0; h->h_sz[root] = n + 1; h->h_parent[root] = -1; h->h_pd[root] = -2;
+    h->h_depth.assign(n + 1, 1); h->h_depth[root] = 0;
+}
+
+// Warm start: the staging arrays from the basis the previous optimal solve left on the device.  The basis is
+// the set of arcs in STATE_TREE plus the flows; parent / pred / direction follow from a traversal from the root, the interval
+// labels are unobservable (any depth-first order is valid), and the potentials are recomputed for the CURRENT costs along the
+// tree: pi[u] = pi[parent] - cost when the pred arc leaves u, + cost when it enters u (reduced cost 0 on every tree arc,
+// NS.cs:1185-1209).  Returns false (caller starts cold) when the arrays do not describe a spanning tree.
+bool build_warm_basis(mcf_handle* h, int64_t art_cost)
+{
+    const int n = h->n, m = h->m, S = m + n, A = m + 2 * n, root = n;
+    std::vector<int> w_state(A);
+    std::vector<long long> w_flow(A);
+    if (cudaMemcpy(w_state.data(), h->d_state.p, (size_t)A * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaMemcpy(w_flow.data(), h->d_flow.p, (size_t)A * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    h->metrics.d2h_bytes += (int64_t)A * 12;
+    build_initial_basis(h, art_cost);                       // arc arrays (endpoints, new costs, capacities) and the second artificial arcs' owners
+    // endpoints of the second set of artificial arcs [S, A): the cold basis hands them out in node order (NS.cs:755-771 / :822-838)
+    const bool geq = h->opt.supply_type == MCF_GEQ;
+    std::vector<int> f_node(A - S, -1);
+    for (int u = 0; u < n; ++u) if ((h->h_pd[u] >> 1) >= S) f_node[(h->h_pd[u] >> 1) - S] = u;
+    auto ends = [&](int a, int& s, int& t) {
+        if (a < S) { s = h->h_src[a]; t = h->h_tgt[a]; return true; }
+        const int u = f_node[a - S];
+        if (u < 0) return false;
+        if (geq) { s = u; t = root; } else { s = root; t = u; }
+        return true;
+    };
+    // adjacency of the tree arcs
+    std::vector<int> deg(n + 2, 0), tree_arcs;
+    tree_arcs.reserve(n);
+    for (int a = 0; a < A; ++a) if (w_state[a] == mcf::STATE_TREE) {
+        int s, t; if (!ends(a, s, t)) return false;
+        tree_arcs.push_back(a); ++deg[s + 1]; ++deg[t + 1];
+    }
+    if ((int)tree_arcs.size() != n) return false;
+    for (int u = 0; u <= n; ++u) deg[u + 1] += deg[u];
+    std::vector<int> adj(2 * (size_t)n), fill(deg.begin(), deg.end() - 1);
+    for (int a : tree_arcs) { int s, t; ends(a, s, t); adj[fill[s]++] = a; adj[fill[t]++] = a; }
+    // depth-first traversal from the root: labels, parent, pred word, depth, potentials
+    std::vector<int> order; order.reserve(n + 1);
+    std::vector<int> stack; stack.reserve(n + 1);
+    std::vector<char> seen(n + 1, 0);
+    h->h_parent[root] = -1; h->h_pd[root] = -2; h->h_depth[root] = 0; h->h_pi[root] = 0;
+    stack.push_back(root); seen[root] = 1;
+    while (!stack.empty()) {
+        const int u = stack.back(); stack.pop_back();
+        h->h_in[u] = (int)order.size(); order.push_back(u);
+        for (int k = deg[u + 1] - 1; k >= deg[u]; --k) {            // pushed in reverse: children are visited in adjacency order
+            const int a = adj[k];
+            int s, t; ends(a, s, t);
+            const int v = s == u ? t : s;
+            if (seen[v]) continue;
+            seen[v] = 1;
+            const bool dir_up = s == v;                             // the arc leaves the child towards its parent
+            const long long c = a < S ? (long long)h->h_cost[a] : (long long)art_cost;
+            h->h_parent[v] = u; h->h_pd[v] = a * 2 + (dir_up ? 1 : 0); h->h_depth[v] = h->h_depth[u] + 1;
+            h->h_pi[v] = dir_up ? h->h_pi[u] - c : h->h_pi[u] + c;
+            stack.push_back(v);
+        }
+    }
+    if ((int)order.size() != n + 1) return false;
+    for (int u = 0; u <= n; ++u) h->h_sz[u] = 1;
+    for (int i = n; i > 0; --i) { const int u = order[i]; h->h_sz[h->h_parent[u]] += h->h_sz[u]; }
+    for (int a = 0; a < A; ++a) { h->h_state[a] = w_state[a]; h->h_flow[a] = w_flow[a]; }
+    for (int e = 0; e < m; ++e) if (h->orig_lower[e] != 0) h->h_flow[e] -= h->orig_lower[e];      // the epilogue added the lower bounds (NS.cs:375-388)
+    return true;
 }
 
 int upload_basis(mcf_handle* h, bool need_cache, int grid)
@@ -390,7 +462,7 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     const size_t seg_off = (w_ent + w_pr + w_late + w_cyc + 7) & ~(size_t)7;
     CUDA_TRY(h, h->d_mail.ensure(seg_off + w_seg + 8));
     h->h_node.resize(n + 1);
-    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = u == n ? 0 : 1; }
+    for (int u = 0; u <= n; ++u) { h->h_node[u].pi = h->h_pi[u]; h->h_node[u].in = h->h_in[u]; h->h_node[u].dp = h->h_depth[u]; }
     cudaStream_t st = h->stream;
     int64_t bytes = 0;
     auto up = [&](void* d, const void* s, size_t b) { bytes += (int64_t)b; return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st); };
@@ -414,6 +486,15 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     return MCF_OK;
 }
 
+
+// after a solve: an Optimal result whose device arrays (state, flow) a later warm start may pick up
+void note_warm(mcf_handle* h, int st)
+{
+    h->warm_valid = false;
+    if (st != MCF_OPTIMAL || !h->opt.warm_start) return;
+    h->warm_upper.swap(h->cur_upper); h->warm_supply.swap(h->cur_supply); h->warm_lower = h->orig_lower; h->warm_supply_type = h->opt.supply_type;
+    h->warm_valid = true;
+}
 
 int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
                clk::time_point t_total, int32_t* status_out, bool* needs_wide)
@@ -517,6 +598,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
         for (int i = 0; i < m; ++i) if (h->orig_lower[i] != 0) { h->supply[h->source[i]] += h->orig_lower[i]; h->supply[h->target[i]] -= h->orig_lower[i]; }
     }
     (void)S;
+    note_warm(h, st);
     return done(st);
 }
 
@@ -700,7 +782,15 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
 
     if (n == 0) { h->flow.assign(m, 0); h->pi.clear(); h->total_cost = 0; return done(MCF_OPTIMAL); }
 
-    build_initial_basis(h, art_cost);
+    bool warm = false;
+    if (h->opt.warm_start) {
+        h->cur_upper = h->upper; h->cur_supply = h->supply;                                           // standard form: what the basis belongs to
+        if (h->warm_valid && h->warm_supply_type == h->opt.supply_type && h->warm_upper == h->cur_upper && h->warm_supply == h->cur_supply && h->warm_lower == h->orig_lower)
+            warm = build_warm_basis(h, art_cost);
+    }
+    h->warm_valid = false;
+    if (!warm) build_initial_basis(h, art_cost);
+    h->metrics.warm_started = warm ? 1 : 0;
     h->metrics.host_prepass_time_us = us_since(t_pre);
 
     // engine: the team engine (node slices resident in shared memory) runs plain Block Search; everything else, and
@@ -815,6 +905,7 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
     if (st == MCF_OPTIMAL && has_lower) {                                                            // NS.cs:375-388 (supplies)
         for (int i = 0; i < m; ++i) if (h->orig_lower[i] != 0) { h->supply[h->source[i]] += h->orig_lower[i]; h->supply[h->target[i]] -= h->orig_lower[i]; }
     }
+    note_warm(h, st);
     return done(st);
 }
 
@@ -961,6 +1052,7 @@ int mcf_pricing_probe(mcf_handle* h, int32_t reps, int32_t flush_l2, float* ms_o
     int rc = bind_device(h);
     if (rc != MCF_OK) return rc;
     h->d_pi_final = nullptr;                                    // the probe re-uploads the initial basis over the solve's arrays
+    h->warm_valid = false;
     const int n = h->n, m = h->m, S = m + n;
     // same pre-pass as mcf_solve, on copies: the probe must not disturb the handle's problem data
     std::vector<int64_t> sv_supply = h->supply, sv_upper = h->upper;

@@ -78,7 +78,7 @@ class _CConfig(C.Structure):
 class _COptions(C.Structure):
     _fields_ = [("supply_type", C.c_int32), ("pivot_rule", C.c_int32), ("auto_configuration", C.c_int32),
                 ("optimized_pivot", C.c_int32), ("device", C.c_int32), ("max_ctas", C.c_int32),
-                ("lookahead_blocks", C.c_int32), ("engine", C.c_int32), ("simd_width", C.c_int32), ("reserved0", C.c_int32),
+                ("lookahead_blocks", C.c_int32), ("engine", C.c_int32), ("simd_width", C.c_int32), ("warm_start", C.c_int32),
                 ("stop_after_pivots", C.c_int64),
                 ("barrier_timeout_s", C.c_double), ("config", _CConfig)]
 
@@ -96,7 +96,7 @@ class SolverMetrics(C.Structure):      # OptimizationTypes.cs:43-69 + engine cou
                 ("config_flags", C.c_int32), ("grid_ctas", C.c_int32), ("degree_cv", C.c_double),
                 ("engine", C.c_int32), ("pricer_ctas", C.c_int32), ("stem_exchanges", C.c_int64),
                 ("hop_wait_done_us", C.c_double), ("stem_exchange_us", C.c_double), ("ns_per_clock", C.c_double),
-                ("phase_us", C.c_double * 16), ("wide_flows", C.c_int32), ("reserved1", C.c_int32)]
+                ("phase_us", C.c_double * 16), ("wide_flows", C.c_int32), ("warm_started", C.c_int32)]
 
     # reference property names
     Iterations = property(lambda s: s.iterations)
@@ -333,6 +333,14 @@ class NetworkSimplex:
         is to reproduce (BlockSearchPivotOptimized.cs:74): 4 on x64 AVX2 (default), 2 on SSE2 / NEON, 0 = not accelerated."""
         self._opt.optimized_pivot = int(bool(enable))
         if simd_width is not None: self._opt.simd_width = int(simd_width)
+
+    def EnableWarmStart(self, enable=True):
+        """SURVEY.md 8f-3 (the reference's README.md:17-18 roadmap item; LEMON's re-run semantics network_simplex.h:836-884): a
+        Solve() that follows an Optimal Solve() on this object after arc-COST edits only (SetArcCost) starts from that optimal basis
+        - tree, arc states, flows kept on the device, potentials recomputed for the new costs - instead of the artificial basis.
+        Any other edit (bounds, supplies, supply type) falls back to a cold start.  GetMetrics().warm_started tells which ran."""
+        self._opt.warm_start = int(bool(enable))
+        return self
 
     def SetMemoryPool(self, pool):          # stored but never read by the reference (NetworkSimplex.cs:541-544)
         pass

@@ -723,6 +723,21 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
         iterations = (int)r->iterations; s->next_arc = r->next_arc; s->block_size = r->block_size;
         s->consecutive_low = r->consecutive_low; s->consecutive_high = r->consecutive_high;
     }
+    if (opt->warm) {                                                          /* warm start: previous optimal basis, new costs */
+        const ns_oracle_state *r = opt->warm;
+        size_t AA = (size_t)m + 2 * (size_t)n;
+        memcpy(s->parent, r->parent, N1 * 4); memcpy(s->pred, r->pred, N1 * 4); memcpy(s->thread, r->thread, N1 * 4);
+        memcpy(s->rev_thread, r->rev_thread, N1 * 4); memcpy(s->succ_num, r->succ_num, N1 * 4); memcpy(s->last_succ, r->last_succ, N1 * 4);
+        memcpy(s->pred_dir, r->pred_dir, N1); memcpy(s->state, r->state, AA); memcpy(s->flow, r->flow, AA * 8);
+        /* reduced cost 0 on every tree arc (the invariant UpdatePotentials maintains, NS.cs:1185-1209), root potential 0,
+         * in thread order so that a parent is set before its children; initialize() above has put the current costs - and the
+         * current artificial cost - on the arcs */
+        s->pi[s->root] = 0;
+        for (int u = s->thread[s->root]; u != s->root; u = s->thread[u]) {
+            int e = s->pred[u], p = s->parent[u];
+            s->pi[u] = s->pred_dir[u] == DIR_UP ? s->pi[p] - s->cost[e] : s->pi[p] + s->cost[e];
+        }
+    }
     int64_t max_iterations = (int64_t)n * m; if (max_iterations < 1000000) max_iterations = 1000000;  /* NS.cs:280 */
     double t_price = 0, t_tree = 0, t_pot = 0;
     const int timing = opt->collect_phase_times;
@@ -768,7 +783,7 @@ int ns_oracle_solve(int n, int m, const int32_t *src, const int32_t *tgt, const 
     if (kind == 2 || kind == 3) res->final_block_size = s->block_size;
     res->pricing_seconds = t_price; res->tree_seconds = t_tree; res->potential_seconds = t_pot;
 
-    if (res->stopped_early && opt->save) {
+    if (opt->save) {
         ns_oracle_state *w = opt->save;
         size_t AA = (size_t)m + 2 * (size_t)n;
         memcpy(w->parent, s->parent, N1 * 4); memcpy(w->pred, s->pred, N1 * 4); memcpy(w->thread, s->thread, N1 * 4);

@@ -57,11 +57,15 @@ typedef struct {
     int32_t *trace_u_out;        /* leaving node per pivot, -1 when the entering arc only flips bound */
     ns_oracle_config config;     /* used when auto_config == 0 (SetOptimizationConfig, NS.cs:557-561) */
     const ns_oracle_state *resume; /* not NULL: continue from this state (its iterations count on; max_pivots is absolute) */
-    ns_oracle_state *save;       /* not NULL: filled with the state when the loop stops at max_pivots */
+    ns_oracle_state *save;       /* not NULL: filled with the state when the loop ends (at max_pivots, or at optimality - before the
+                                    lower bounds are added back to the flows) */
     int32_t emulate_stackalloc;  /* 1: zero-fill an int[n] scratch on every stem re-hang like the reference's
                                     `stackalloc int[_nodeCount]` (NS.cs:1085; no SkipLocalsInit) - timing fidelity only.
                                     Default 0 = the scratch is hoisted (what a C/C++ port would do; conservative baseline). */
     int32_t _pad2;
+    const ns_oracle_state *warm; /* not NULL: WARM START from the basis a previous Optimal solve of the same network with
+                                    other arc costs saved: tree, arc states and flows are taken over, the potentials are recomputed
+                                    along the tree for the current costs, pivot-rule state and counters start fresh */
 } ns_oracle_options;
 
 typedef struct {

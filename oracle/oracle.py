@@ -93,7 +93,7 @@ class Options(C.Structure):
                 ("auto_config", C.c_int32), ("simd_width", C.c_int32), ("collect_phase_times", C.c_int32),
                 ("max_pivots", C.c_int64), ("trace_capacity", C.c_int64),
                 ("trace_in_arc", C.c_void_p), ("trace_u_out", C.c_void_p), ("config", Config),
-                ("resume", C.c_void_p), ("save", C.c_void_p), ("emulate_stackalloc", C.c_int32), ("_pad2", C.c_int32)]
+                ("resume", C.c_void_p), ("save", C.c_void_p), ("emulate_stackalloc", C.c_int32), ("_pad2", C.c_int32), ("warm", C.c_void_p)]
 
 
 class Result(C.Structure):
@@ -161,7 +161,7 @@ def select_config(ch: Characteristics) -> Config:
 
 def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config: Config | None = None,
           optimized_pivot=False, simd_width=4, max_pivots=0, trace=0, phase_times=False, resume: State | None = None,
-          save: State | None = None, emulate_stackalloc=False):
+          save: State | None = None, emulate_stackalloc=False, warm: State | None = None):
     """Returns (Result, flow[int64 m], pi[int64 n], trace_in_arc | None, trace_u_out | None)."""
     src, tgt, lo, up, co, su = _arrs(p)
     o = Options()
@@ -179,11 +179,14 @@ def solve(p, pivot_rule=BLOCK_SEARCH, supply_type=GEQ, auto_config=True, config:
         c_res = resume.c(); o.resume = C.addressof(c_res)
     if save is not None:
         c_save = save.c(); o.save = C.addressof(c_save)
+    c_warm = None
+    if warm is not None:
+        c_warm = warm.c(); o.warm = C.addressof(c_warm)
     res = Result()
     flow = np.zeros(p.m, np.int64); pi = np.zeros(p.n, np.int64)
     lib().ns_oracle_solve(C.c_int(p.n), C.c_int(p.m), _p(src), _p(tgt), _p(lo), _p(up), _p(co), _p(su),
                           C.byref(o), C.byref(res), _p(flow), _p(pi))
-    if save is not None and res.stopped_early:
+    if save is not None:
         save.take(c_save)
     return res, flow, pi, tin, tout
 

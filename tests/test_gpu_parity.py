@@ -415,6 +415,67 @@ def test_list_rules_prefix_at_2_20(rule):
     check_prefix_parity(instances.netgen8(20), rule, 60000)
 
 
+def _warm_case(p, rule, engine, frac, seed, lower=False):
+    """Solve, edit `frac` of the arc costs, solve again warm on the GPU and on the oracle: same pivots, flows, potentials."""
+    import copy
+    if lower:                                       # lower bounds: the basis flows live in the shifted (standard) form
+        p = copy.copy(p); p.lower = np.where((np.arange(p.m) % 7 == 0) & (p.upper >= 2), 1, 0).astype(np.int64)   # (lower == upper trips the reference's `delta == 0` unbounded test, NS.cs:321)
+    ns = mcf.NetworkSimplex.from_problem(p)
+    ns.SetPivotRule(rule).SetOptimizationConfig(mcf.OptimizationConfig()); ns.EnableWarmStart(True)
+    if engine is not None:
+        ns.set_engine_options(engine=engine)
+    st = oracle.State(p.n, p.m)
+    r0, f0, pi0, _, _ = oracle.solve(p, pivot_rule=int(rule), config=_oracle_cfg(mcf.OptimizationConfig()), save=st)
+    assert ns.Solve() == mcf.SolverStatus.Optimal and r0.status == 1
+    assert ns.GetMetrics().warm_started == 0 and ns.GetMetrics().iterations == r0.iterations and np.array_equal(ns.flows(), f0)
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(p.m, max(1, int(p.m * frac)), replace=False)
+    new = rng.integers(1, int(p.cost.max()) + 1, idx.size)
+    p2 = copy.copy(p); p2.cost = p.cost.copy(); p2.cost[idx] = new
+    for e, c in zip(idx[:50], new[:50]):
+        ns.SetArcCost(mcf.Arc(int(e)), int(c))                      # the reference's per-arc setter
+    ns.set_arrays(p2.lower, p2.upper, p2.cost, p2.supply)           # ... and the bulk form for the rest
+    rw, fw, piw, _, _ = oracle.solve(p2, pivot_rule=int(rule), config=_oracle_cfg(mcf.OptimizationConfig()), warm=st)
+    rc, fc, pic, _, _ = oracle.solve(p2, pivot_rule=int(rule), config=_oracle_cfg(mcf.OptimizationConfig()))
+    assert ns.Solve() == mcf.SolverStatus.Optimal and rw.status == 1
+    M = ns.GetMetrics()
+    tag = (p.name, int(rule), engine, frac)
+    assert M.warm_started == 1, tag
+    assert M.iterations == rw.iterations, (tag, M.iterations, rw.iterations, rc.iterations)
+    assert ns.GetTotalCost() == rw.total_cost == rc.total_cost, tag
+    assert np.array_equal(ns.flows(), fw) and np.array_equal(ns.potentials(), piw), tag
+    assert oracle.validate(p2, ns.flows(), ns.potentials(), ns.GetTotalCost())[0] == 0, tag
+    assert rw.iterations < rc.iterations, (tag, rw.iterations, rc.iterations)
+    return ns, p2, rw, rc
+
+
+def test_warm_start_after_cost_edits():
+    """SURVEY.md 8f-3 (README.md:17-18 roadmap, LEMON re-run semantics network_simplex.h:836-884): a re-solve after arc-cost edits
+    starts from the previous optimal basis kept on the device.  Both engines, several rules, with and without lower bounds: pivot
+    count, every flow and potential equal the oracle's warm start; fewer pivots than a cold solve of the edited problem."""
+    p = instances.netgen8(14)
+    _warm_case(p, mcf.PivotRule.BlockSearch, "team", 0.01, 1)
+    _warm_case(p, mcf.PivotRule.BlockSearch, "flat", 0.01, 2)
+    _warm_case(p, mcf.PivotRule.BlockSearch, "team", 0.002, 3, lower=True)
+    _warm_case(p, mcf.PivotRule.FirstEligible, None, 0.01, 4)
+    _warm_case(instances.netgen8(11), mcf.PivotRule.BestEligible, None, 0.02, 5)
+    _warm_case(p, mcf.PivotRule.CandidateList, None, 0.01, 6, lower=True)
+    _warm_case(p, mcf.PivotRule.AlteringList, None, 0.01, 7)
+    _warm_case(instances.grid_time_expanded(96, 96), mcf.PivotRule.BlockSearch, "team", 0.01, 8)
+    ns, p2, rw, rc = _warm_case(instances.netgen8(16), mcf.PivotRule.BlockSearch, None, 0.001, 9)
+    # unchanged problem: the kept basis is optimal, zero pivots
+    assert ns.Solve() == mcf.SolverStatus.Optimal and ns.GetMetrics().warm_started == 1 and ns.GetMetrics().iterations == 0
+    assert ns.GetTotalCost() == rw.total_cost
+    # a capacity edit invalidates the basis: cold start, == the oracle's cold solve
+    import copy
+    p3 = copy.copy(p2); p3.upper = p2.upper.copy(); p3.upper[::97] = np.maximum(1, p3.upper[::97] // 2)
+    ns.set_arrays(p3.lower, p3.upper, p3.cost, p3.supply)
+    r3, f3, pi3, _, _ = oracle.solve(p3, config=_oracle_cfg(mcf.OptimizationConfig()))
+    assert int(ns.Solve()) == r3.status and ns.GetMetrics().warm_started == 0 and ns.GetMetrics().iterations == r3.iterations
+    if r3.status == 1:
+        assert np.array_equal(ns.flows(), f3) and np.array_equal(ns.potentials(), pi3)
+
+
 def test_batch_of_64_instances_of_2_18_nodes():
     """BASELINE.json config 5 itself on one GPU: 64 independent NETGEN-8 2^18-node instances, four side by side; every instance
     bit-exact against what the CPU oracle recorded (tests/golden/batch18.json: pivots, cost, sha256 of flow[] and pi[])."""

@@ -207,3 +207,26 @@ def test_list_rule_parameters_and_list_mechanics():
     rc, *_ = oracle.solve(p, pivot_rule=oracle.CANDIDATE_LIST, auto_config=False)
     ra, *_ = oracle.solve(p, pivot_rule=oracle.ALTERING_LIST, auto_config=False)
     assert rb.total_cost == rc.total_cost == ra.total_cost and len({rb.iterations, rc.iterations, ra.iterations}) == 3
+
+
+def test_oracle_warm_start_reaches_the_cold_optimum():
+    """Warm start (the reference lists it as future work, README.md:17-18, so no vector exists): from the saved
+    optimal basis of the same network the oracle must (i) need zero pivots and reproduce every potential when nothing changed,
+    (ii) after cost edits reach the optimum a cold solve finds - same cost, validator-clean - in fewer pivots."""
+    import copy
+    from mincostflow_b200 import instances
+    p = instances.netgen8(12)
+    st = oracle.State(p.n, p.m)
+    r0, f0, pi0, _, _ = oracle.solve(p, auto_config=False, save=st)
+    rz, fz, piz, _, _ = oracle.solve(p, auto_config=False, warm=st)
+    assert rz.status == 1 and rz.iterations == 0 and np.array_equal(fz, f0) and np.array_equal(piz, pi0)
+    rng = np.random.default_rng(11)
+    idx = rng.choice(p.m, p.m // 50, replace=False)
+    p2 = copy.copy(p); p2.cost = p.cost.copy(); p2.cost[idx] = rng.integers(1, 10000, idx.size)
+    for rule in (oracle.FIRST_ELIGIBLE, oracle.BLOCK_SEARCH, oracle.CANDIDATE_LIST, oracle.ALTERING_LIST):
+        rc, fc, pic, _, _ = oracle.solve(p2, pivot_rule=rule, auto_config=False)
+        rw, fw, piw, _, _ = oracle.solve(p2, pivot_rule=rule, auto_config=False, warm=st)
+        assert rw.status == rc.status == 1 and rw.total_cost == rc.total_cost and rw.iterations < rc.iterations, rule
+        assert oracle.validate(p2, fw, piw, rw.total_cost)[0] == 0, rule
+        if oracle.lemon_available():
+            assert oracle.lemon_solve(p2)["cost"] == rw.total_cost
