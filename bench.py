@@ -265,7 +265,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "pivots_per_s", "value": value, "unit": "pivots/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-           "config": {"workload": workload_name(args.workload), "sample": sample_txt},
+           "config": {"workload": workload_name(args.workload)},        # (the sample is described in cpu_baseline.sample: same `config` as our arm)
            "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": 1, "kind": "port", "sample": sample_txt, **host_info(),
                             **recorded_full_cpu(p.name)},
            "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

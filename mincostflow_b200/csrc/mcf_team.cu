@@ -132,6 +132,7 @@ struct TeamShared {
     PWin win;                       // entering arc of this pivot
     int4 rec[kMaxPricers][7];       // pricing records as received
     int ncand, nstem, abort, cnt;
+    int wide_req;                   // narrow mode: a flow of this slice left the int32 range; travels in the next CYC record
     int pre[kTeamMax + 1];
 };
 
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
         }
         if (!pricer) for (int j = cntn + tid; j < P.slice; j += kTT) { in_s[j] = 0; sz_s[j] = 0; dp_s[j] = 0; pd_s[j] = -2; fl_s[j] = 0; up_s[j] = 0; }   // padding: on no cycle, never relabelled
-        if (tid == 0) { sh.abort = 0; Book z = {}; sh.bk = z; }
-        if (__syncthreads_or(bad)) { if (tid == 0) P.ctl->needs_wide = 1; }
+        if (tid == 0) { sh.abort = 0; sh.wide_req = 0; Book z = {}; sh.bk = z; }
+        if (__syncthreads_or(bad)) { if (tid == 0) { P.ctl->needs_wide = 1; sh.wide_req = 1; } }
     }
     if (tid == 0) { sh.bk.t_begin = gtimer(); sh.bk.c_begin = sh.bk.t_mark = sh.bk.pr_mark = (unsigned long long)clock64(); }
 
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             // the record goes out in kRepCyc copies (lane l writes word l % 5 of copy l / 5)
             int4* const rec = P.cyc + (((size_t)par * kRepCyc + lane / 5) * G + cta) * kMailWords;
             if (nc == 0) {
-                if (tid < 5 * kRepCyc) st_vol4(rec + lane % 5, make_int4(0, 0, 0, seq));
+                if (tid < 5 * kRepCyc) st_vol4(rec + lane % 5, make_int4(0, sh.wide_req ? 16 : 0, 0, seq));
             } else {
                 Cand m1 = cand_none(), m2 = cand_none();
                 if (nc <= kCandCap) {
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (warp == 0 && lane < 5 * kRepCyc) {
                     const int wd = lane % 5;
                     int4 w;
-                    if (wd == 0) w = make_int4(nc, (m1.zero & 1) | ((m2.zero & 1) << 1) | (m1.pd >= 0 ? 4 : 0) | (m2.pd >= 0 ? 8 : 0), 0, seq);
+                    if (wd == 0) w = make_int4(nc, (m1.zero & 1) | ((m2.zero & 1) << 1) | (m1.pd >= 0 ? 4 : 0) | (m2.pd >= 0 ? 8 : 0) | (sh.wide_req ? 16 : 0), 0, seq);
                     else if (wd == 1) w = make_int4(lo32(m1.d), hi32(m1.d), m1.in, seq);
                     else if (wd == 2) w = make_int4(m1.sz, m1.pd, m1.dp, seq);
                     else if (wd == 3) w = make_int4(lo32(m2.d), hi32(m2.d), m2.in, seq);
@@ -780,6 +781,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 unsigned spins = 0; long long t0 = 0;
                 while ((int)(ld_vol_u32(p) - want) < 0) if (spin_check(spins, t0, P)) { sh.abort = 1; break; }
             }
+            int wreq = 0;
             if (warp < nw) {
                 Cand b1 = cand_none(), b2 = cand_none();
                 int c = 0;
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                     int4 w[5];
                     if (!poll_rec<5>(P.cyc + (((size_t)par * kRepCyc + cta % kRepCyc) * G + NP + tid) * kMailWords, seq, w, P)) sh.abort = 1;
                     else {
-                        c = w[0].x;
+                        c = w[0].x; wreq = w[0].y & 16;
                         if (w[0].y & 4) { b1.d = mk64(w[1].x, w[1].y); b1.in = w[1].z; b1.sz = w[2].x; b1.pd = w[2].y; b1.dp = w[2].z; b1.zero = w[0].y & 1; }
                         if (w[0].y & 8) { b2.d = mk64(w[3].x, w[3].y); b2.in = w[3].z; b2.sz = w[4].x; b2.pd = w[4].y; b2.dp = w[4].z; b2.zero = (w[0].y >> 1) & 1; }
                     }
@@ -800,8 +802,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                 if (l1 >= 0 && lane == l1) sh.wc[0][warp] = b1;
                 if (l2 >= 0 && lane == l2) sh.wc[1][warp] = b2;
             }
-            __syncthreads();
+            // narrow mode: some owner saw a flow leave the int32 range during update k-1.  The flag arrives with the CYC records, so
+            // every CTA of the team leaves the loop on this same pivot and the host re-runs wide at once (the narrow
+            // solve used to carry on with truncated flows until it ended by itself).
+            const int any_wide = __syncthreads_or(wreq);
             if (sh.abort) [[unlikely]] { status = ST_ERR_BARRIER_TIMEOUT; break; }
+            if (any_wide) [[unlikely]] { status = ST_ERR_NEEDS_WIDE; break; }
             Cand w1 = cand_none(), w2 = cand_none();
             for (int w = 0; w < nw; ++w) {
                 const Cand t1 = sh.wc[0][w], t2 = sh.wc[1][w];
@@ -969,7 +975,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         }
                     }
                 }
-                if (bad) P.ctl->needs_wide = 1;
+                if (bad) { P.ctl->needs_wide = 1; sh.wide_req = 1; }
                 // hop 3: everything this CTA wrote for pivot k is visible before DONE(k)
                 PROBE(13);
                 __syncthreads();

@@ -18,7 +18,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "pivots_per_s" and d["unit"] == "pivots/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "int64" and d["data"] == "synthetic"
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert list(d["config"]) == ["workload"]                      # same `config` as the GPU arm's workload; the sample is in cpu_baseline
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
