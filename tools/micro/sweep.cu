@@ -33,6 +33,7 @@ template <int HINT> __device__ __forceinline__ int ld_stream1(const int* base, i
     else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(base + e), "l"(pol));
     return v;
 }
+__device__ __forceinline__ long long ld_pi_l1(const long long* pi, int u) { return __ldg(pi + u); }
 template <int HINT> __device__ __forceinline__ long long ld_pi(const long long* pi, int u, unsigned long long pol)
 {
     long long v;
@@ -82,10 +83,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quad(const Arrays A, Best* ou
         for (int u = 0; u < NQ; ++u) {
             pt[u][0] = st[u].x ? ld_pi<HINT>(A.pi, t[u].x, pl) : 0; pt[u][1] = st[u].y ? ld_pi<HINT>(A.pi, t[u].y, pl) : 0;
             pt[u][2] = st[u].z ? ld_pi<HINT>(A.pi, t[u].z, pl) : 0; pt[u][3] = st[u].w ? ld_pi<HINT>(A.pi, t[u].w, pl) : 0;
+            if (HINT == 3) {
+                ps[u][0] = ld_pi_l1(A.pi, s[u].x);
+                ps[u][1] = s[u].y == s[u].x ? ps[u][0] : ld_pi_l1(A.pi, s[u].y);
+                ps[u][2] = s[u].z == s[u].y ? ps[u][1] : ld_pi_l1(A.pi, s[u].z);
+                ps[u][3] = s[u].w == s[u].z ? ps[u][2] : ld_pi_l1(A.pi, s[u].w);
+            } else {
             ps[u][0] = ld_pi<HINT>(A.pi, s[u].x, pl);
             ps[u][1] = s[u].y == s[u].x ? ps[u][0] : ld_pi<HINT>(A.pi, s[u].y, pl);
             ps[u][2] = s[u].z == s[u].y ? ps[u][1] : ld_pi<HINT>(A.pi, s[u].z, pl);
             ps[u][3] = s[u].w == s[u].z ? ps[u][2] : ld_pi<HINT>(A.pi, s[u].w, pl);
+            }
         }
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
@@ -164,12 +172,161 @@ __global__ void __launch_bounds__(THREADS, MINB) k_arc(const Arrays A, Best* out
     block_min_out(brc, barc, out);
 }
 
+
+// ---- variant B: the four arc streams go global -> shared by bulk async copies (cp.async.bulk / UBLKCP: the TMA engine, no L1TEX
+// sectors, no registers), a ring of NS chunks of CH arcs per CTA; the last warp out of a chunk refills its stage.  A thread
+// handles CH / THREADS arcs of a chunk (positions t, t + THREADS, ...: conflict-free shared-memory reads).  GATHER 0 = stream only.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+template <int THREADS, int MINB, int CH, int NS, int GATHER>
+__global__ void __launch_bounds__(THREADS, MINB) k_bulk(const Arrays A, Best* out)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    int* const ring = reinterpret_cast<int*>(dyn);                                   // [NS][4][CH]
+    unsigned long long* const full = reinterpret_cast<unsigned long long*>(dyn + (size_t)NS * 4 * CH * 4);
+    int* const outc = reinterpret_cast<int*>(full + NS);
+    constexpr int PER = CH / THREADS, NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, S = A.S;
+    const int nchunk = (S + CH - 1) / CH;
+    const int mine = blockIdx.x < nchunk ? (nchunk - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // chunks blockIdx.x, + gridDim.x, ...
+    auto issue = [&](int i) {
+        const int c = blockIdx.x + i * gridDim.x, lo = c * CH, len = S - lo < CH ? S - lo : CH, s = i % NS;
+        const unsigned bytes = (unsigned)len * 4u;                                  // S is a multiple of 4 here: 16-byte granules
+        mbar_expect_tx(full + s, 4u * bytes);
+        int* const st = ring + (size_t)s * 4 * CH;
+        bulk_g2s(st, A.src + lo, bytes, full + s); bulk_g2s(st + CH, A.tgt + lo, bytes, full + s);
+        bulk_g2s(st + 2 * CH, A.cost + lo, bytes, full + s); bulk_g2s(st + 3 * CH, A.state + lo, bytes, full + s);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); outc[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < NS && i < mine; ++i) issue(i);
+    }
+    __syncthreads();
+    long long brc = 0; int barc = INT_MAX;
+    for (int i = 0; i < mine; ++i) {
+        const int s = i % NS;
+        const unsigned parity = (unsigned)(i / NS) & 1u;
+        while (!mbar_try_wait(full + s, parity)) { }
+        const int c = blockIdx.x + i * gridDim.x, lo = c * CH;
+        const int* const st = ring + (size_t)s * 4 * CH;
+        int vs[PER], vt[PER], vc[PER], vst[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int q = tid + u * THREADS;
+            const bool in = lo + q < S;
+            vs[u] = in ? st[q] : 0; vt[u] = in ? st[CH + q] : 0; vc[u] = in ? st[2 * CH + q] : 0; vst[u] = in ? st[3 * CH + q] : 0;
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(outc + s, 1) == NW - 1) {          // every warp has its values in registers: refill the stage
+            outc[s] = 0;
+            if (i + NS < mine) { asm volatile("fence.proxy.async;" ::: "memory"); issue(i + NS); }
+        }
+        if (GATHER) {
+            long long d[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) d[u] = __ldcg(A.pi + vs[u]) - (vst[u] ? __ldcg(A.pi + vt[u]) : 0);
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const long long r = (long long)vst[u] * ((long long)vc[u] + d[u]);
+                if (r < brc) { brc = r; barc = lo + tid + u * THREADS; }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < PER; ++u) { const long long r = -(long long)(((vs[u] ^ vt[u] ^ vc[u] ^ vst[u]) & 0x3fffff)) - 1; if (r < brc) { brc = r; barc = lo + tid + u * THREADS; } }
+        }
+    }
+    block_min_out(brc, barc, out);
+}
+
+// ---- variant W: variant B with a rolling window - a thread keeps the arcs of W chunks in registers with their gathers in flight
+// (slot k is retired right before it is refilled, W chunks later), so the gathers never drain at a chunk boundary while the ring
+// stays small (the shared memory comes out of the L1 that tracks the gathers' misses).
+template <int THREADS, int MINB, int CH, int NS, int W>
+__global__ void __launch_bounds__(THREADS, MINB) k_bulkw(const Arrays A, Best* out)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    int* const ring = reinterpret_cast<int*>(dyn);                                   // [NS][4][CH]
+    unsigned long long* const full = reinterpret_cast<unsigned long long*>(dyn + (size_t)NS * 4 * CH * 4);
+    int* const outc = reinterpret_cast<int*>(full + NS);
+    constexpr int PER = CH / THREADS, NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, S = A.S;
+    const int nchunk = (S + CH - 1) / CH;
+    const int mine = blockIdx.x < nchunk ? (nchunk - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    auto issue = [&](int i) {
+        const int c = blockIdx.x + i * gridDim.x, lo = c * CH, len = S - lo < CH ? S - lo : CH, s = i % NS;
+        const unsigned bytes = (unsigned)len * 4u;
+        mbar_expect_tx(full + s, 4u * bytes);
+        int* const st = ring + (size_t)s * 4 * CH;
+        bulk_g2s(st, A.src + lo, bytes, full + s); bulk_g2s(st + CH, A.tgt + lo, bytes, full + s);
+        bulk_g2s(st + 2 * CH, A.cost + lo, bytes, full + s); bulk_g2s(st + 3 * CH, A.state + lo, bytes, full + s);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); outc[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < NS && i < mine; ++i) issue(i);
+    }
+    __syncthreads();
+    long long brc = 0; int barc = INT_MAX;
+    int wc[W][PER], wst[W][PER], wlo[W]; long long wps[W][PER], wpt[W][PER];
+#pragma unroll
+    for (int k = 0; k < W; ++k) { wlo[k] = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { wc[k][u] = 0; wst[k][u] = 0; wps[k][u] = 0; wpt[k][u] = 0; } }
+    for (int i0 = 0; i0 < mine + W; i0 += W) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int i = i0 + k;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {                                         // retire what slot k holds (state 0 = nothing)
+                const long long r = (long long)wst[k][u] * ((long long)wc[k][u] + wps[k][u] - wpt[k][u]);
+                if (r < brc) { brc = r; barc = wlo[k] + tid + u * THREADS; }
+                wst[k][u] = 0;
+            }
+            if (i < mine) {
+                const int s = i % NS;
+                const unsigned parity = (unsigned)(i / NS) & 1u;
+                while (!mbar_try_wait(full + s, parity)) { }
+                const int lo = (blockIdx.x + i * gridDim.x) * CH;
+                const int* const st = ring + (size_t)s * 4 * CH;
+                int vs[PER], vt[PER];
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int q = tid + u * THREADS;
+                    const bool in = lo + q < S;
+                    vs[u] = in ? st[q] : 0; vt[u] = in ? st[CH + q] : 0; wc[k][u] = in ? st[2 * CH + q] : 0; wst[k][u] = in ? st[3 * CH + q] : 0;
+                }
+                wlo[k] = lo;
+                __syncwarp();
+                if (lane == 0 && atomicAdd(outc + s, 1) == NW - 1) {
+                    outc[s] = 0;
+                    if (i + NS < mine) { asm volatile("fence.proxy.async;" ::: "memory"); issue(i + NS); }
+                }
+#pragma unroll
+                for (int u = 0; u < PER; ++u) { wps[k][u] = __ldcg(A.pi + vs[u]); wpt[k][u] = wst[k][u] ? __ldcg(A.pi + vt[u]) : 0; }
+            }
+        }
+    }
+    block_min_out(brc, barc, out);
+}
+
 __global__ void init_arcs(int* src, int* tgt, int* cost, int* state, long long* pi, int m, int n)
 {
     const int S = m + n;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S; e += gridDim.x * blockDim.x) {
         unsigned long long x = (unsigned long long)e * 0x9E3779B97F4A7C15ULL; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
-        if (e < m) { src[e] = e >> 3; tgt[e] = (int)(x % (unsigned)n); cost[e] = 1 + (int)((x >> 33) % 10000u); state[e] = (x >> 50) & 1 ? 1 : -1; }
+        if (e < m) { src[e] = (int)(((long long)(e >> 3) * 5) % n);   /* runs of 8 arcs per source, every source in its own 32-byte sector (as NETGEN-8: 16.5 source sectors per 128 arcs) */ tgt[e] = (int)(x % (unsigned)n); cost[e] = 1 + (int)((x >> 33) % 10000u); state[e] = (x >> 50) & 1 ? 1 : -1; }
         else { src[e] = e - m; tgt[e] = n; cost[e] = 0; state[e] = 0; }
     }
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u <= n; u += gridDim.x * blockDim.x) {
@@ -187,15 +344,17 @@ __global__ void __launch_bounds__(512) l2_read(const int4* buf, size_t n4, long 
 static Arrays g_A; static Best* g_out; static void* g_flush; static const size_t kFb = 256u << 20; static long long* g_sink;
 static long long g_ref_rc = 1; static int g_ref_arc = -2;
 
-template <typename K> void bench(const char* name, K kern, int grid, int threads)
+static int g_check = 1;
+template <typename K> void bench(const char* name, K kern, int grid, int threads, size_t smem = 0)
 {
+    if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     std::vector<float> ms;
     for (int r = 0; r < 11; ++r) {
         cudaMemsetAsync(g_flush, r, kFb);
         l2_read<<<148 * 4, 512>>>((const int4*)((char*)g_flush + kFb), kFb / 16, g_sink);
         cudaEventRecord(e0);
-        kern<<<grid, threads>>>(g_A, g_out);
+        kern<<<grid, threads, smem>>>(g_A, g_out);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float t; cudaEventElapsedTime(&t, e0, e1); ms.push_back(t);
     }
@@ -208,7 +367,7 @@ template <typename K> void bench(const char* name, K kern, int grid, int threads
     std::sort(ms.begin(), ms.end());
     const float t = ms[ms.size() / 2];
     printf("%-34s grid %5d x %4d : median %6.1f us  min %6.1f us  %7.1f GB/s  frac-of-6545 %.3f  %s%s\n", name, grid, threads, t * 1e3, ms[0] * 1e3,
-           16.0 * g_A.S / 1e6 / t, 16.0 * g_A.S / 1e6 / t / 6545.3, (rc == g_ref_rc && arc == g_ref_arc) ? "ok" : "MISMATCH", err == cudaSuccess ? "" : cudaGetErrorString(err));
+           16.0 * g_A.S / 1e6 / t, 16.0 * g_A.S / 1e6 / t / 6545.3, !g_check ? "(stream only)" : (rc == g_ref_rc && arc == g_ref_arc) ? "ok" : "MISMATCH", err == cudaSuccess ? "" : cudaGetErrorString(err));
     fflush(stdout);
 }
 
@@ -223,6 +382,17 @@ int main()
     g_A.src = src; g_A.tgt = tgt; g_A.cost = cost; g_A.state = state; g_A.pi = pi; g_A.S = S;
     const int sms = 148;
 #define RUN(expr, grid, thr) bench(#expr, expr, grid, thr)
+#define RUNB(T, MB, CH, NS, Gt) { g_check = Gt; bench("k_bulk<" #T "," #MB "," #CH "," #NS "," #Gt ">", k_bulk<T, MB, CH, NS, Gt>, sms * MB, T, (size_t)NS * 16 * CH + 16 * NS + 64); g_check = 1; }
+    RUN((k_quad<1, 0, 1024, 1>), sms, 1024);                 // reference result + the shipped shape
+    RUN((k_quad<1, 3, 1024, 1>), sms, 1024);                 // pi[source] through L1
+    RUN((k_quad<1, 3, 512, 4>), sms * 4, 512);
+    RUNB(256, 4, 1024, 2, 0) RUNB(256, 4, 1024, 3, 0) RUNB(512, 2, 2048, 2, 0) RUNB(1024, 1, 4096, 2, 0) RUNB(256, 4, 512, 4, 0) RUNB(128, 8, 512, 2, 0) RUNB(256, 2, 1024, 4, 0)
+    RUNB(256, 4, 1024, 2, 1) RUNB(256, 4, 1024, 3, 1) RUNB(512, 2, 2048, 2, 1) RUNB(1024, 1, 4096, 2, 1) RUNB(256, 4, 512, 4, 1) RUNB(128, 8, 512, 2, 1) RUNB(256, 2, 1024, 4, 1)
+    RUNB(256, 8, 512, 2, 1) RUNB(256, 6, 1024, 2, 1) RUNB(512, 3, 2048, 2, 1) RUNB(512, 4, 1024, 2, 1)
+#define RUNW(T, MB, CH, NS, W) bench("k_bulkw<" #T "," #MB "," #CH "," #NS "," #W ">", k_bulkw<T, MB, CH, NS, W>, sms * MB, T, (size_t)NS * 16 * CH + 16 * NS + 64);
+    RUNW(512, 2, 1024, 2, 3) RUNW(512, 2, 1024, 2, 4) RUNW(256, 4, 512, 2, 3) RUNW(1024, 1, 2048, 2, 3) RUNW(1024, 1, 2048, 2, 4) RUNW(512, 2, 1024, 3, 3)
+    RUNW(256, 4, 1024, 2, 2) RUNW(512, 2, 2048, 2, 2) RUNW(512, 2, 512, 2, 6) RUNW(512, 2, 512, 4, 6) RUNW(1024, 1, 1024, 2, 6) RUNW(1024, 1, 1024, 4, 6) RUNW(1024, 1, 1024, 4, 8)
+    RUNW(512, 3, 1024, 2, 3) RUNW(512, 4, 512, 2, 4) RUNW(256, 8, 256, 2, 4)
     RUN((k_pipe<0, 1024, 1>), sms, 1024);                    // the r01 kernel's shape
     RUN((k_pipe<1, 1024, 1>), sms, 1024);
     RUN((k_pipe<2, 1024, 1>), sms, 1024);

@@ -1,4 +1,4 @@
-"""Short team-engine run for ncu source-level captures.  Usage: python tools/profile_team.py [log2n=13] [pivots=3000]"""
+"""Short team-engine run for ncu source-level captures.  Usage: python tools/profile_team.py [log2n=13] [pivots=3000] [pricing CTAs=auto]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,7 +9,7 @@ piv = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
 p = instances.netgen8(k)
 ns = mcf.NetworkSimplex.from_problem(p)
 ns.SetOptimizationConfig(mcf.OptimizationConfig())
-ns.set_engine_options(stop_after_pivots=piv, engine="team", barrier_timeout_s=5.0)
+ns.set_engine_options(stop_after_pivots=piv, engine="team", barrier_timeout_s=5.0, lookahead_blocks=int(sys.argv[3]) if len(sys.argv) > 3 else None)
 ns.Solve()
 M = ns.GetMetrics()
 print(json.dumps(dict(pivots=M.iterations, us_per_pivot=M.kernel_time_us / max(M.iterations, 1), grid=M.grid_ctas,
