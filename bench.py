@@ -151,6 +151,7 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.skip = 0
 
     def start(self):
         try:
@@ -160,6 +161,10 @@ class ClockSampler:
             self.t.start()
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """The timed region starts here: earlier samples are dropped."""
+        self.skip = len(self.lines)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -174,7 +179,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in (self.lines[self.skip:] or self.lines[-1:]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -345,10 +350,13 @@ def run_ours(args):
             assert all(v["ok"] and v["status"] == 1 for v in got.values()), {i: (v["status"], v["ok"]) for i, v in got.items()}
         return ms, (len(got) if got is not None else 0)
 
+    # nvidia-smi is started before the warm-up (its start-up takes 0.2-0.3 s and holds driver locks, which would land inside a
+    # sub-second timed region); only the samples taken after the timed region begins are used
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
         step(bounded=True)
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
+    sampler.mark()
     t0 = time.perf_counter()
     tot_piv = tot_kus = tot_h2d = tot_d2h = tot_launch = 0
     gather_ms = 0.0; gathered_n = 0

@@ -35,8 +35,14 @@ namespace {
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
 constexpr int kPf = 4;                                  // arcs per pricer thread staged ahead (2048 per pricing CTA)
-constexpr int kRepEnt = 4;                              // replicas of every ENTER record: a reader polls replica (cta % kRepEnt)
-constexpr int kRepCyc = 6;                              // replicas of every CYC record (fewer pollers per line, profiles/r01_micro_hop.txt)
+#ifndef MCF_REP_ENT
+#define MCF_REP_ENT 4
+#endif
+#ifndef MCF_REP_CYC
+#define MCF_REP_CYC 6
+#endif
+constexpr int kRepEnt = MCF_REP_ENT;                    // replicas of every ENTER record: a reader polls replica (cta % kRepEnt)
+constexpr int kRepCyc = MCF_REP_CYC;                    // replicas of every CYC record (fewer pollers per line, profiles/r01_micro_hop.txt)
 constexpr int kRelUnroll = 4;                            // nodes per thread in flight in the relabel pass
 constexpr int kCandCap = 32;                            // cycle nodes of one slice handled by the single-warp path
 
