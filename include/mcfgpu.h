@@ -91,7 +91,8 @@ typedef struct mcf_options {
     int32_t device;                 /* CUDA device ordinal */
     int32_t max_ctas;               /* 0 = one CTA per SM (cooperative-launch limit) */
     int32_t lookahead_blocks;       /* flat engine: blocks priced in the first pricing round (0 = 2); team engine: pricing CTAs (0 = auto) */
-    int32_t engine;                 /* 0 = automatic; 1 = flat engine (mcf_kernels.cu); 2 = team engine (mcf_team.cu, Block Search) */
+    int32_t engine;                 /* 0 = automatic; 1 = flat engine (mcf_kernels.cu); 2 = team engine (mcf_team.cu, Block Search); 3 = team engine
+                                       with the tree-arc flows in global memory (what 0 / 2 fall back to when the resident slices do not fit) */
     int32_t simd_width;             /* optimized Block Search only: Vector<long>.Count of the host whose pivot sequence is to be
                                        reproduced (BlockSearchPivotOptimized.cs:74, :119): 4 = x64 AVX2 (default), 2 = SSE2 / NEON,
                                        0 = Vector.IsHardwareAccelerated false.  With a non-zero width the reference's scalar loop
@@ -137,7 +138,7 @@ typedef struct mcf_metrics {
     double stem_exchange_us;
     double ns_per_clock;                /* team engine: measured SM clock period */
     double phase_us[16];                /* team engine: sub-phase times (0-7 pricing CTA, 8-15 first owner CTA), see DESIGN.md */
-    int32_t wide_flows;                 /* team engine: 1 = tree-arc flows resident as int64, 0 = int32 */
+    int32_t wide_flows;                 /* team engine: bit 0 = tree-arc flows kept as int64 (else int32); bit 1 = kept in global memory (else in the slices) */
     int32_t warm_started;               /* 1 = this solve started from the previous optimal basis (mcf_options.warm_start) */
 } mcf_metrics;
 

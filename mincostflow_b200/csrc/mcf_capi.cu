@@ -28,9 +28,9 @@ extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t st
 extern "C" int mcfk_launch_l2_read(const void* buf, size_t bytes, long long* sink, int sms, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaStream_t stream);
-extern "C" size_t mcfk_team_smem_bytes(int slice, int wide);
-extern "C" int mcfk_team_max_slice(int device, int wide);
-extern "C" int mcfk_team_max_ctas(int device, int slice, int wide);
+extern "C" size_t mcfk_team_smem_bytes(int slice, int wide, int spill);
+extern "C" int mcfk_team_max_slice(int device, int wide, int spill);
+extern "C" int mcfk_team_max_ctas(int device, int slice, int wide, int spill);
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream);
 extern "C" void mcfk_team_replicas(int* ent, int* cyc);
 
@@ -96,7 +96,7 @@ struct mcf_handle {
     DevBuf<mcf::NodeRec> d_node;
     DevBuf<int4> d_mail;                                              // ent0 | prc | late | cyc | stemseg
     DevBuf<unsigned> d_done;
-    DevBuf<long long> d_piout;
+    DevBuf<long long> d_piout, d_flg, d_upg;
     std::vector<mcf::NodeRec> h_node;
     // warm start (mcf_options.warm_start): what identifies the problem the device arrays of the last optimal solve belong to
     bool warm_valid = false;
@@ -248,7 +248,7 @@ int bind_device(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_flg.release(); h->d_upg.release(); h->d_cand.release(); h->d_cand_scratch.release(); h->d_cand_cost.release(); h->d_val.release(); h->d_pi_final = nullptr;
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->device_bound = dev;
     }
@@ -409,11 +409,11 @@ int choose_grid(mcf_handle* h, int* sms_out)
 
 // Team engine (mcf_team.cu): the first `pricers` CTAs price, the others own node slices that stay in shared memory.
 // Returns the team size, 0 when the instance does not fit (caller falls back to the flat engine).
-int choose_team(mcf_handle* h, int wide, int* slice_out, int* pricers_out)
+int choose_team(mcf_handle* h, int wide, int spill, int* slice_out, int* pricers_out)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->opt.device) != cudaSuccess) return 0;
-    const int max_slice = mcfk_team_max_slice(h->opt.device, wide);
+    const int max_slice = mcfk_team_max_slice(h->opt.device, wide, spill);
     if (max_slice <= 0) return 0;
     int limit = prop.multiProcessorCount;
     if (limit > mcf::kTeamMax) limit = mcf::kTeamMax;
@@ -437,12 +437,12 @@ int choose_team(mcf_handle* h, int wide, int* slice_out, int* pricers_out)
     slice = (slice + 7) & ~7LL;
     if (slice > max_slice) return 0;
     const int team = (int)(owners + pricers);
-    if (mcfk_team_max_ctas(h->opt.device, (int)slice, wide) < team) return 0;
+    if (mcfk_team_max_ctas(h->opt.device, (int)slice, wide, spill) < team) return 0;
     *slice_out = (int)slice; *pricers_out = (int)pricers;
     return team;
 }
 
-int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::TeamParams* P)
+int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, int spill, mcf::TeamParams* P)
 {
     const int n = h->n, m = h->m, S = m + n, A = m + 2 * n;
     CUDA_TRY(h, h->d_src.ensure(S + 4)); CUDA_TRY(h, h->d_tgt.ensure(S + 4)); CUDA_TRY(h, h->d_cost.ensure(S + 4));
@@ -483,6 +483,12 @@ int upload_team(mcf_handle* h, int team, int pricers, int slice, int wide, mcf::
     P->ent0 = h->d_mail.p; P->prc = P->ent0 + w_ent; P->late = P->prc + w_pr; P->cyc = P->late + w_late;
     P->stemseg = h->d_mail.p + seg_off;
     P->done = h->d_done.p; P->ctl = h->d_ctl.p; P->team = team; P->pricers = pricers; P->slice = slice; P->wide = wide;
+    P->spill = spill;
+    if (spill) {                                        // flows / capacities of the tree arcs, one entry per node, each touched by its owner only
+        const size_t ents = (size_t)(team - pricers) * slice + 8;
+        CUDA_TRY(h, h->d_flg.ensure(ents)); CUDA_TRY(h, h->d_upg.ensure(ents));
+        P->fl_g = h->d_flg.p; P->up_g = h->d_upg.p;
+    }
     return MCF_OK;
 }
 
@@ -496,7 +502,7 @@ void note_warm(mcf_handle* h, int st)
     h->warm_valid = true;
 }
 
-int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
+int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int spill, int block, int dyn_min, const mcf_optimization_config& cfg, bool has_lower,
                clk::time_point t_total, int32_t* status_out, bool* needs_wide)
 {
     const int n = h->n, m = h->m, S = m + n;
@@ -504,7 +510,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     h->metrics.grid_ctas = team;
     const auto t_h2d = clk::now();
     mcf::TeamParams P;
-    int rc = upload_team(h, team, pricers, slice, wide, &P);
+    int rc = upload_team(h, team, pricers, slice, wide, spill, &P);
     if (rc != MCF_OK) return rc;
     if (has_lower) {
         CUDA_TRY(h, h->d_lower.ensure(m));
@@ -568,7 +574,7 @@ int solve_team(mcf_handle* h, int team, int pricers, int slice, int wide, int bl
     M.iterations = ctl.iterations; M.total_arcs_checked = ctl.arcs_checked; M.final_block_size = ctl.final_block_size;
     M.average_arcs_checked_per_pivot = ctl.iterations > 0 ? (double)ctl.arcs_checked / ctl.iterations : 0;
     M.iteration_ratio = M.baseline_iterations > 0 ? (double)ctl.iterations / M.baseline_iterations : 1.0;
-    M.pricer_ctas = pricers; M.wide_flows = wide;
+    M.pricer_ctas = pricers; M.wide_flows = wide | (spill ? 2 : 0);
     // phase accumulators are SM clock ticks (reading %globaltimer costs microseconds); scale by the kernel's own ns / tick
     const double ns_per_clk = ctl.clk_total > 0 ? (double)ctl.ns_total / (double)ctl.clk_total : 0.0;
     M.pivot_search_time_us = ctl.ns_price * ns_per_clk / 1000.0; M.cycle_time_us = ctl.ns_cycle * ns_per_clk / 1000.0;
@@ -655,7 +661,7 @@ void mcf_destroy(mcf_handle* h)
         h->d_src.release(); h->d_tgt.release(); h->d_cost.release(); h->d_state.release(); h->d_in.release(); h->d_sz.release();
         h->d_parent.release(); h->d_pd.release(); h->d_flow.release(); h->d_upper.release(); h->d_lower.release(); h->d_pi.release();
         h->d_rc.release(); h->d_part.release(); h->d_list.release(); h->d_scratch.release(); h->d_ctl.release(); h->d_flush.release();
-        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_val.release(); h->d_pi_final = nullptr;
+        h->d_node.release(); h->d_mail.release(); h->d_done.release(); h->d_piout.release(); h->d_flg.release(); h->d_upg.release(); h->d_cand.release(); h->d_cand_scratch.release(); h->d_cand_cost.release(); h->d_val.release(); h->d_pi_final = nullptr;
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -805,16 +811,28 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
             int64_t pos = 0;
             for (int u = 0; u < n; ++u) { const int64_t a = h->supply[u] < 0 ? -h->supply[u] : h->supply[u]; pos += a; if (pos >= (int64_t)std::numeric_limits<int32_t>::max()) { wide = 1; break; } }
         }
+        // per flow width: the slices with the tree-arc flows resident, else with the flows in global memory (16 B per node resident:
+        // n up to ~1.5 M, and 2^20 nodes with 64-bit flows); opt.engine == 3 asks for the second form (tests)
+        // The shared memory of the slices comes out of the SM's L1, and the pricing CTAs (same launch, same carve-out) gather the
+        // next block's node records through it: with the flows resident a 2^20-node instance leaves 34 KB of L1 and runs at
+        // 7.2 us per pivot, with the flows in global memory 97 KB and 6.8 us (profiles/r02_team_tuning.txt; below ~2^19 nodes the
+        // resident form is 1-2 % faster).  So: resident while the slices stay under kResidentMax, else spilled.
+        constexpr size_t kResidentMax = 160u << 10;
         for (; wide < 2; ++wide) {
-            int slice = 0, pricers = 0;
-            const int team = choose_team(h, wide, &slice, &pricers);
+            int slice = 0, pricers = 0, spill = h->opt.engine == 3 ? 1 : 0;
+            int team = choose_team(h, wide, spill, &slice, &pricers);
+            if (!spill && (team <= 0 || mcfk_team_smem_bytes(slice, wide, 0) > kResidentMax)) {
+                int s2 = 0, p2 = 0;
+                const int t2 = choose_team(h, wide, 1, &s2, &p2);
+                if (t2 > 0) { team = t2; slice = s2; pricers = p2; spill = 1; }
+            }
             if (team <= 0) break;
             bool needs_wide = false;
-            rc = solve_team(h, team, pricers, slice, wide, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
+            rc = solve_team(h, team, pricers, slice, wide, spill, block, dyn_min, cfg, has_lower, t_total, status_out, &needs_wide);
             if (rc != MCF_OK || !needs_wide) return rc;
         }
-        if (h->opt.engine == 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but the instance does not fit (n = %d)", n);
-    } else if (h->opt.engine == 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but not applicable (pricing kind %d)", kind);
+        if (h->opt.engine >= 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but the instance does not fit (n = %d)", n);
+    } else if (h->opt.engine >= 2) return fail(h, MCF_ERR_ENGINE_LIMIT, "team engine requested but not applicable (pricing kind %d)", kind);
 
     int sms = 0;
     const int grid = choose_grid(h, &sms);

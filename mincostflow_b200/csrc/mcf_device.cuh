@@ -119,11 +119,11 @@ struct __align__(16) NodeRec {          // global mirror of a node, read by the 
 
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
-constexpr int kMaxPricers = 16;         // pricing CTAs of a team
+constexpr int kMaxPricers = 32;         // pricing CTAs of a team
 constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages
 
 // per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
-constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32;
+constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32, kNodeSmemSpill = 16;
 
 struct TeamParams {
     int n, m, S, A;
@@ -147,6 +147,10 @@ struct TeamParams {
     int pricers;
     int slice;                                           // nodes per owner
     int wide;                                            // 1: tree-arc flows / capacities resident as int64, 0: int32
+    int spill;                                           // 1: flows / capacities of the tree arcs live in global memory (fl_g / up_g, touched for the
+                                                         // ~30 cycle nodes of a pivot only) and a slice keeps 16 B per node: instances past the
+                                                         // resident capacity (n > 1.05 M, or 2^20 nodes with 64-bit flows) still run on this engine
+    void* fl_g; void* up_g;                              // [owners x slice] of int (narrow) or long long (wide); entry of node u at index u
     int block_size, dyn_min_block, max_block_size, adaptive, consecutive;
     double low_thr, high_thr, shrink, grow;
     long long max_iterations, stop_after;

@@ -249,9 +249,11 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const st_up = st_pd + kTeamStemCap;                                    // capacity of that arc (INT_MAX: infinite, -1: fetch)
     unsigned char* const body = reinterpret_cast<unsigned char*>(st_up + kTeamStemCap);
     // owners
-    F* const fl_s = reinterpret_cast<F*>(body);                                 // flow on the pred arc of node j
-    F* const up_s = fl_s + P.slice;                                             // capacity of the pred arc
-    int* const in_s = reinterpret_cast<int*>(up_s + P.slice);
+    // (spill mode: the two arrays below are this owner's part of a global array instead - same code, generic addressing; only the
+    // cycle nodes of a pivot ever touch them, and only their owner does)
+    F* const fl_s = P.spill ? reinterpret_cast<F*>(P.fl_g) + lo : reinterpret_cast<F*>(body);                 // flow on the pred arc of node j
+    F* const up_s = P.spill ? reinterpret_cast<F*>(P.up_g) + lo : reinterpret_cast<F*>(body) + P.slice;       // capacity of the pred arc
+    int* const in_s = P.spill ? reinterpret_cast<int*>(body) : reinterpret_cast<int*>(reinterpret_cast<F*>(body) + 2 * (size_t)P.slice);
     int* const sz_s = in_s + P.slice;
     int* const pd_s = sz_s + P.slice;
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
@@ -1052,21 +1054,23 @@ constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (3 * 8 + 8 * 4);
 inline const void* team_fn(int wide) { return wide ? (const void*)mcf::ns_team_kernel<long long> : (const void*)mcf::ns_team_kernel<int>; }
 }  // namespace
 
-extern "C" size_t mcfk_team_smem_bytes(int slice, int wide)
+static inline int node_bytes(int wide, int spill) { return spill ? mcf::kNodeSmemSpill : wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow; }
+
+extern "C" size_t mcfk_team_smem_bytes(int slice, int wide, int spill)
 {
-    const size_t owner = (size_t)slice * (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
+    const size_t owner = (size_t)slice * node_bytes(wide, spill);
     return kStemBytes + (owner > kPricerBytes ? owner : kPricerBytes) + 16;
 }
 
 // largest slice (nodes per owner CTA) that fits the opt-in shared memory of the device next to the kernel's static part
-extern "C" int mcfk_team_max_slice(int device, int wide)
+extern "C" int mcfk_team_max_slice(int device, int wide, int spill)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, team_fn(wide)) != cudaSuccess) return -2;
     const long long avail = (long long)prop.sharedMemPerBlockOptin - (long long)fa.sharedSizeBytes - (long long)kStemBytes - 64;
-    const long long s = avail / (wide ? mcf::kNodeSmemWide : mcf::kNodeSmemNarrow);
+    const long long s = avail / node_bytes(wide, spill);
     return (int)(s & ~7LL);
 }
 
@@ -1083,11 +1087,11 @@ static cudaError_t raise_smem_limit(int device, int wide)
     return cudaFuncSetAttribute(team_fn(wide), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes));
 }
 
-extern "C" int mcfk_team_max_ctas(int device, int slice, int wide)
+extern "C" int mcfk_team_max_ctas(int device, int slice, int wide, int spill)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
-    const size_t smem = mcfk_team_smem_bytes(slice, wide);
+    const size_t smem = mcfk_team_smem_bytes(slice, wide, spill);
     if (raise_smem_limit(device, wide) != cudaSuccess) return -2;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, team_fn(wide), mcf::kTT, smem) != cudaSuccess) return -3;
@@ -1098,7 +1102,7 @@ extern "C" void mcfk_team_replicas(int* ent, int* cyc) { *ent = mcf::kRepEnt; *c
 
 extern "C" int mcfk_launch_team(const mcf::TeamParams* p, cudaStream_t stream)
 {
-    const size_t smem = mcfk_team_smem_bytes(p->slice, p->wide);
+    const size_t smem = mcfk_team_smem_bytes(p->slice, p->wide, p->spill);
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e == cudaSuccess) e = raise_smem_limit(device, p->wide);

@@ -367,7 +367,7 @@ class NetworkSimplex:
         return self
 
     def set_engine_options(self, max_ctas=None, lookahead_blocks=None, stop_after_pivots=None, barrier_timeout_s=None, device=None, engine=None):
-        if engine is not None: self._opt.engine = {"auto": 0, "flat": 1, "team": 2}.get(engine, engine)
+        if engine is not None: self._opt.engine = {"auto": 0, "flat": 1, "team": 2, "team_spill": 3}.get(engine, engine)
         if max_ctas is not None: self._opt.max_ctas = int(max_ctas)
         if lookahead_blocks is not None: self._opt.lookahead_blocks = int(lookahead_blocks)
         if stop_after_pivots is not None: self._opt.stop_after_pivots = int(stop_after_pivots)

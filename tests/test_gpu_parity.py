@@ -254,6 +254,26 @@ def test_both_engines_and_both_flow_widths():
     assert ns.GetMetrics().wide_flows == 1
 
 
+def test_team_engine_with_flows_in_global_memory():
+    """The team engine's second form (engine = 3 / "team_spill"; what the automatic choice falls back to when the resident slices do
+    not fit: n > 1.05 M, or 2^20 nodes with 64-bit flows - r01 verdict "capacity cliff"): full parity on NETGEN, the grid, the deep
+    chain, narrow and wide flows; and the 2^20 instance with one capacity >= 2^31 (wide) runs on the team engine, not the flat one."""
+    cfg = mcf.OptimizationConfig()
+    for p in (instances.netgen8(14), instances.grid_time_expanded(64, 64), deep_chain(4000)):
+        ns, _ = check_parity(p, cfg=cfg, engine="team_spill")
+        assert ns.GetMetrics().engine == 2 and ns.GetMetrics().wide_flows == 2
+    p = instances.netgen8(12)
+    big = Problem(p.n, p.m, p.source, p.target, p.lower, np.where(np.arange(p.m) % 5 == 0, 2 ** 33, p.upper).astype(np.int64), p.cost, p.supply, "netgen12_wide")
+    ns, _ = check_parity(big, cfg=cfg, engine="team_spill")
+    assert ns.GetMetrics().wide_flows == 3
+    p20 = instances.netgen8(20)
+    up = p20.upper.copy(); up[12345] = 2 ** 33
+    big20 = Problem(p20.n, p20.m, p20.source, p20.target, p20.lower, up, p20.cost, p20.supply, "netgen20_wide")
+    ns = check_prefix_parity(big20, mcf.PivotRule.BlockSearch, 150000)
+    M = ns.GetMetrics()
+    assert M.engine == 2 and M.wide_flows == 3, (M.engine, M.wide_flows)
+
+
 def test_team_engine_multi_block_searches_and_adaptive_blocks(load_fixture):
     """Searches that run past the first block (pricer-per-block rounds, the late ENTER record), the final full sweep, and the
     adaptive block size changing under the staged pricing pipeline."""
