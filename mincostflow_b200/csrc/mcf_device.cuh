@@ -120,10 +120,16 @@ struct __align__(16) NodeRec {          // global mirror of a node, read by the 
 constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one 128-byte line)
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
 constexpr int kMaxPricers = 32;         // pricing CTAs of a team
-constexpr int kTeamStemCap = 1024;      // longest stem the team engine stages
+#ifndef MCF_STEM_CAP
+#define MCF_STEM_CAP 256
+#endif
+#ifndef MCF_SPILL_DP
+#define MCF_SPILL_DP 1
+#endif
+constexpr int kTeamStemCap = MCF_STEM_CAP;   // longest stem the team engine stages in shared memory (longer ones are read in place)
 
 // per resident node: in, sz, pd, depth (int) + flow and capacity of its pred arc (int32 in narrow mode, int64 in wide mode)
-constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32, kNodeSmemSpill = 16;
+constexpr int kNodeSmemNarrow = 24, kNodeSmemWide = 32, kNodeSmemSpill = MCF_SPILL_DP ? 12 : 16;   // spill: in, sz, pd (+ depth)
 
 struct TeamParams {
     int n, m, S, A;

@@ -34,7 +34,10 @@ namespace {
 
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
-constexpr int kPf = 4;                                  // arcs per pricer thread staged ahead (2048 per pricing CTA)
+#ifndef MCF_PF
+#define MCF_PF 2
+#endif
+constexpr int kPf = MCF_PF;                             // arcs per pricer thread staged ahead (kPf x 512 per pricing CTA)
 #ifndef MCF_REP_ENT
 #define MCF_REP_ENT 4
 #endif
@@ -257,6 +260,9 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
     int* const sz_s = in_s + P.slice;
     int* const pd_s = sz_s + P.slice;
     int* const dp_s = pd_s + P.slice;                                           // depth in the basis tree
+    // spill mode: the depth is read from the node mirror, which this CTA alone writes (NodeRec::dp), instead of a resident copy
+    const bool dp_res = !(MCF_SPILL_DP && P.spill);
+    auto dp_get = [&](int j) -> int { return dp_res ? dp_s[j] : P.node[lo + j].dp; };
     // pricers: arc data and both ends' node records of this pricer's share of the staged block
     constexpr int kStage = kPf * kTT;
     long long* const pf_up = reinterpret_cast<long long*>(body);
@@ -277,12 +283,12 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
         for (int j = tid; j < cntn; j += kTT) {
             const int u = lo + j;
             const int pd = P.pd0[u];
-            in_s[j] = P.in_g[u]; dp_s[j] = P.node[u].dp; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
+            in_s[j] = P.in_g[u]; if (dp_res) dp_s[j] = P.node[u].dp; sz_s[j] = P.sz0[u]; pd_s[j] = pd;
             const long long fl = pd >= 0 ? P.flow[pd >> 1] : 0, up = pd >= 0 ? P.upper[pd >> 1] : 0;
             bad |= !FT::fits(fl);
             fl_s[j] = (F)fl; up_s[j] = FT::cap_in(up);
         }
-        if (!pricer) for (int j = cntn + tid; j < P.slice; j += kTT) { in_s[j] = 0; sz_s[j] = 0; dp_s[j] = 0; pd_s[j] = -2; fl_s[j] = 0; up_s[j] = 0; }   // padding: on no cycle, never relabelled
+        if (!pricer) for (int j = cntn + tid; j < P.slice; j += kTT) { in_s[j] = 0; sz_s[j] = 0; if (dp_res) dp_s[j] = 0; pd_s[j] = -2; fl_s[j] = 0; up_s[j] = 0; }   // padding: on no cycle, never relabelled
         if (tid == 0) { sh.abort = 0; sh.wide_req = 0; Book z = {}; sh.bk = z; }
         if (__syncthreads_or(bad)) { if (tid == 0) { P.ctl->needs_wide = 1; sh.wide_req = 1; } }
     }
@@ -693,7 +699,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
             const bool dir_up = pd & 1;
             // first walk: residual capacity when pred_dir == DOWN, else the flow; second walk mirrored (NS.cs:968, :986)
             const bool increase = hasF ? !dir_up : dir_up;
-            Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd; cd.dp = dp_s[j]; cd.j = j;
+            Cand cd; cd.d = increase ? FT::residual(up, fl) : (long long)fl; cd.in = in_u; cd.sz = sz_u; cd.pd = pd; cd.dp = dp_get(j); cd.j = j;
             cd.zero = (((!increase) || up == 0) ? 1 : 0) | (hasF ? 2 : 0);
             return cd;
         };
@@ -876,7 +882,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                             const int in_u = in_s[j], sz_u = sz_s[j];
                             const bool hasF = (unsigned)(inF - in_u) < (unsigned)sz_u;
                             const bool hasS = (unsigned)(inS - in_u) < (unsigned)sz_u;
-                            if (hasF != hasS && hasF == in_side1 && in_u >= a) publish(j, in_u, sz_u, pd_s[j], dp_s[j], hasF);
+                            if (hasF != hasS && hasF == in_side1 && in_u >= a) publish(j, in_u, sz_u, pd_s[j], dp_get(j), hasF);
                         }
                     }
                 }
@@ -955,7 +961,7 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                         const int x = in_s[j], sz_u = sz_s[j];
                         const bool hasF = (unsigned)(inF - x) < (unsigned)sz_u;
                         const bool hasS = (unsigned)(inS - x) < (unsigned)sz_u;
-                        if (hasF != hasS) update_cycle_node(j, x, sz_u, pd_s[j], dp_s[j], hasF);
+                        if (hasF != hasS) update_cycle_node(j, x, sz_u, pd_s[j], dp_get(j), hasF);
                     }
                     __syncthreads();                                                    // the relabel pass below rewrites in_s
                 }
@@ -975,8 +981,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
                                 in_s[j] = x + sh_by; P.in_g[lo + j] = x + sh_by;
                             } else if ((unsigned)(x - a) < (unsigned)s) {                  // re-hung subtree
                                 int nx, nd;
-                                relabel(U, x, dp_s[j], nx, nd);
-                                in_s[j] = nx; dp_s[j] = nd;
+                                relabel(U, x, dp_get(j), nx, nd);
+                                in_s[j] = nx; if (dp_res) dp_s[j] = nd;
                                 atomicAdd(reinterpret_cast<unsigned long long*>(&P.node[lo + j].pi), (unsigned long long)U.sigma);
                                 P.in_g[lo + j] = nx; P.node[lo + j].dp = nd;
                             }
