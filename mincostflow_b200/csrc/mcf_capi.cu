@@ -814,14 +814,19 @@ int mcf_solve(mcf_handle* h, int32_t* status_out)
         // per flow width: the slices with the tree-arc flows resident, else with the flows in global memory (16 B per node resident:
         // n up to ~1.5 M, and 2^20 nodes with 64-bit flows); opt.engine == 3 asks for the second form (tests)
         // The shared memory of the slices comes out of the SM's L1, and the pricing CTAs (same launch, same carve-out) gather the
-        // next block's node records through it: with the flows resident a 2^20-node instance leaves 34 KB of L1 and runs at
-        // 7.2 us per pivot, with the flows in global memory 97 KB and 6.8 us (profiles/r02_team_tuning.txt; below ~2^19 nodes the
-        // resident form is 1-2 % faster).  So: resident while the slices stay under kResidentMax, else spilled.
+        // next block's node records through it: with the flows resident a 2^20-node instance leaves 34 KB of L1, with the flows in
+        // global memory 97 KB.  Over FULL solves (profiles/r02_team_tuning.txt): NETGEN-8 2^20 7.94 -> 7.68 us per pivot, but the
+        // 1024^2 time-expanded grid 11.8 -> 13.0 - its cycles are thousands of nodes long and every cycle node's flow then comes
+        // from global memory.  So the spilled form is chosen when the resident slices would leave less than ~64 KB of L1 AND the
+        // graph is dense enough (m >= 6 n) for shallow basis trees and short cycles to be the rule - and whenever the resident
+        // form does not fit at all.
         constexpr size_t kResidentMax = 160u << 10;
+        const bool short_cycles = (int64_t)m >= 6 * (int64_t)n;
         for (; wide < 2; ++wide) {
             int slice = 0, pricers = 0, spill = h->opt.engine == 3 ? 1 : 0;
             int team = choose_team(h, wide, spill, &slice, &pricers);
-            if (!spill && (team <= 0 || mcfk_team_smem_bytes(slice, wide, 0) > kResidentMax)) {
+            const bool force_resident = std::getenv("MCF_FORCE_RESIDENT") != nullptr;                     // tuning aid
+            if (!spill && (team <= 0 || (mcfk_team_smem_bytes(slice, wide, 0) > kResidentMax && short_cycles && !force_resident))) {
                 int s2 = 0, p2 = 0;
                 const int t2 = choose_team(h, wide, 1, &s2, &p2);
                 if (t2 > 0) { team = t2; slice = s2; pricers = p2; spill = 1; }

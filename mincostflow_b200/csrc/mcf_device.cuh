@@ -121,10 +121,10 @@ constexpr int kMailWords = 8;           // 16-byte words per mailbox record (one
 constexpr int kTeamMax = 160;           // upper bound on CTAs in a team (>= SM count)
 constexpr int kMaxPricers = 32;         // pricing CTAs of a team
 #ifndef MCF_STEM_CAP
-#define MCF_STEM_CAP 256
+#define MCF_STEM_CAP 1024
 #endif
 #ifndef MCF_SPILL_DP
-#define MCF_SPILL_DP 1
+#define MCF_SPILL_DP 0
 #endif
 constexpr int kTeamStemCap = MCF_STEM_CAP;   // longest stem the team engine stages in shared memory (longer ones are read in place)
 

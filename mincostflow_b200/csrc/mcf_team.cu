@@ -35,7 +35,7 @@ namespace {
 constexpr int kTT = 512;                                // threads per CTA: latency-bound code, up to 128 registers each
 constexpr int kTW = kTT / 32;
 #ifndef MCF_PF
-#define MCF_PF 2
+#define MCF_PF 4
 #endif
 constexpr int kPf = MCF_PF;                             // arcs per pricer thread staged ahead (kPf x 512 per pricing CTA)
 #ifndef MCF_REP_ENT
