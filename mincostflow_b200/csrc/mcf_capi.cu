@@ -28,6 +28,7 @@ extern "C" int mcfk_launch_pivot(const mcf::Params* p, int grid, cudaStream_t st
 extern "C" int mcfk_launch_l2_read(const void* buf, size_t bytes, long long* sink, int sms, cudaStream_t stream);
 extern "C" int mcfk_launch_price_sweep(const mcf::Params* p, mcf::PriceRec* out, int grid, cudaStream_t stream);
 extern "C" int mcfk_launch_validate(const mcf::ValidateParams* v, int sms, cudaStream_t stream);
+extern "C" cudaError_t mcfk_device_props(int device, cudaDeviceProp* out);
 extern "C" size_t mcfk_team_smem_bytes(int slice, int wide, int spill);
 extern "C" int mcfk_team_max_slice(int device, int wide, int spill);
 extern "C" int mcfk_team_max_ctas(int device, int slice, int wide, int spill);
@@ -151,7 +152,7 @@ struct EventPair {                  // two timing events that are destroyed on e
 bool device_ok(int dev)
 {
     cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return false;
+    if (mcfk_device_props(dev, &p) != cudaSuccess) return false;
     return p.major == 10;           // sm_100a code only
 }
 
@@ -412,7 +413,7 @@ int choose_grid(mcf_handle* h, int* sms_out)
 int choose_team(mcf_handle* h, int wide, int spill, int* slice_out, int* pricers_out)
 {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, h->opt.device) != cudaSuccess) return 0;
+    if (mcfk_device_props(h->opt.device, &prop) != cudaSuccess) return 0;
     const int max_slice = mcfk_team_max_slice(h->opt.device, wide, spill);
     if (max_slice <= 0) return 0;
     int limit = prop.multiProcessorCount;
@@ -1045,7 +1046,7 @@ int mcf_solve_batch_concurrent(mcf_handle** hs, int32_t count, const int32_t* de
         workers.emplace_back([&, w]() {
             const int d = w % n_devices;
             int sms = 0;
-            if (per_device > 1) { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, devices[d]) == cudaSuccess) sms = prop.multiProcessorCount; }
+            if (per_device > 1) { cudaDeviceProp prop; if (mcfk_device_props(devices[d], &prop) == cudaSuccess) sms = prop.multiProcessorCount; }
             for (int i = w; i < count; i += lanes) {
                 if (!hs[i]) { rcs[w] = MCF_ERR_INVALID_ARGUMENT; continue; }
                 const mcf_options saved = hs[i]->opt;                       // device and CTA share are per-call choices, not handle state
@@ -1150,7 +1151,7 @@ int mcf_validate(mcf_handle* h, int32_t* failed_checks_out, int64_t* primal_out,
     V.src = h->d_src.p; V.tgt = h->d_tgt.p; V.cost = h->d_cost.p; V.flow = h->d_flow.p; V.lower = d_lower; V.upper = d_upper;
     V.supply = d_supply; V.pi = h->d_pi_final; V.net = d_net; V.adj = d_adj; V.out = d_out;
     cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device_bound));
+    CUDA_TRY(h, mcfk_device_props(h->device_bound, &prop));
     const int lrc = mcfk_launch_validate(&V, prop.multiProcessorCount, h->stream);
     if (lrc != 0) return fail(h, MCF_ERR_CUDA, "validator launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
     long long out[3] = {0, 0, 0};

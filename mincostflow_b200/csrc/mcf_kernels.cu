@@ -17,6 +17,7 @@
 //
 // Mutable arrays are read with ld.global.cg (L2) after each barrier; static arc arrays go through ld.global.nc.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <limits.h>
 #include <stdint.h>
 
@@ -1185,6 +1186,24 @@ __global__ void __launch_bounds__(256) ns_validate_nodes_kernel(const ValidatePa
 
 // ------------------------------------------------------------------------------------------------ launchers
 
+// cudaGetDeviceProperties takes milliseconds (it queries the whole device, PCIe state included) and used to run five times per
+// solve: one cached copy per device serves every caller of the library.
+extern "C" cudaError_t mcfk_device_props(int device, cudaDeviceProp* out)
+{
+    static cudaDeviceProp cache[64];
+    static int have[64] = {0};
+    static std::mutex mu;
+    if (device < 0 || device >= 64) return cudaGetDeviceProperties(out, device);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[device]) {
+        const cudaError_t e = cudaGetDeviceProperties(&cache[device], device);
+        if (e != cudaSuccess) return e;
+        have[device] = 1;
+    }
+    *out = cache[device];
+    return cudaSuccess;
+}
+
 extern "C" int mcfk_pivot_smem_bytes() { return mcf::kListSmem * (int)sizeof(mcf::CycEnt); }
 
 extern "C" int mcfk_max_grid(int device, int* sm_count)
@@ -1192,7 +1211,7 @@ extern "C" int mcfk_max_grid(int device, int* sm_count)
     int dev = device, sms = 0, per_sm = 0;
     if (cudaGetDeviceCount(&sms) != cudaSuccess) return -1;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    if (mcfk_device_props(dev, &prop) != cudaSuccess) return -1;
     const int smem = mcfk_pivot_smem_bytes();
     if (cudaFuncSetAttribute(mcf::ns_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcf::ns_pivot_kernel, mcf::kThreads, smem) != cudaSuccess) return -3;

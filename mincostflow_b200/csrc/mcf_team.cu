@@ -1054,6 +1054,8 @@ __global__ void __launch_bounds__(kTT, 1) ns_team_kernel(const TeamParams P)
 
 // ------------------------------------------------------------------------------------------------ launchers
 
+extern "C" cudaError_t mcfk_device_props(int device, cudaDeviceProp* out);      // mcf_kernels.cu: cached cudaGetDeviceProperties
+
 namespace {
 constexpr size_t kStemBytes = (size_t)mcf::kTeamStemCap * (8 + 4 * 4);
 constexpr size_t kPricerBytes = (size_t)mcf::kPf * mcf::kTT * (3 * 8 + 8 * 4);
@@ -1072,7 +1074,7 @@ extern "C" size_t mcfk_team_smem_bytes(int slice, int wide, int spill)
 extern "C" int mcfk_team_max_slice(int device, int wide, int spill)
 {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    if (mcfk_device_props(device, &prop) != cudaSuccess) return -1;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, team_fn(wide)) != cudaSuccess) return -2;
     const long long avail = (long long)prop.sharedMemPerBlockOptin - (long long)fa.sharedSizeBytes - (long long)kStemBytes - 64;
@@ -1085,7 +1087,7 @@ extern "C" int mcfk_team_max_slice(int device, int wide, int spill)
 static cudaError_t raise_smem_limit(int device, int wide)
 {
     cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    cudaError_t e = mcfk_device_props(device, &prop);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, team_fn(wide));
@@ -1096,7 +1098,7 @@ static cudaError_t raise_smem_limit(int device, int wide)
 extern "C" int mcfk_team_max_ctas(int device, int slice, int wide, int spill)
 {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    if (mcfk_device_props(device, &prop) != cudaSuccess) return -1;
     const size_t smem = mcfk_team_smem_bytes(slice, wide, spill);
     if (raise_smem_limit(device, wide) != cudaSuccess) return -2;
     int per_sm = 0;
