@@ -496,6 +496,39 @@ def test_warm_start_after_cost_edits():
         assert np.array_equal(ns.flows(), f3) and np.array_equal(ns.potentials(), pi3)
 
 
+def test_random_small_networks_every_rule_and_warm_start():
+    """80 random small networks (infeasible ones, lower bounds, negative costs): every pivot rule incl. the two list rules bit-exact
+    against the oracle (status, pivots, flows, potentials), then a warm re-solve after random cost edits against the oracle's."""
+    import copy
+    from conftest import random_small_problem
+    rng = np.random.default_rng(20261019)
+    cfg = mcf.OptimizationConfig()
+    warm_checked = 0
+    for case in range(80):
+        p = random_small_problem(rng, case)
+        if p is None:
+            continue
+        for rule in (mcf.PivotRule.FirstEligible, mcf.PivotRule.BestEligible, mcf.PivotRule.BlockSearch, mcf.PivotRule.CandidateList, mcf.PivotRule.AlteringList):
+            check_parity(p, rule, cfg=cfg)
+        rule = (mcf.PivotRule.BlockSearch, mcf.PivotRule.CandidateList, mcf.PivotRule.AlteringList)[case % 3]
+        st = oracle.State(p.n, p.m)
+        r0, *_ = oracle.solve(p, pivot_rule=int(rule), config=_oracle_cfg(cfg), save=st)
+        if r0.status != 1:
+            continue
+        ns = mcf.NetworkSimplex.from_problem(p)
+        ns.SetPivotRule(rule).SetOptimizationConfig(cfg); ns.EnableWarmStart(True)
+        assert ns.Solve() == mcf.SolverStatus.Optimal
+        p2 = copy.copy(p); p2.cost = p.cost.copy()
+        idx = rng.choice(p.m, max(1, p.m // 5), replace=False); p2.cost[idx] = rng.integers(1, 40, idx.size)
+        ns.set_arrays(p2.lower, p2.upper, p2.cost, p2.supply)
+        rw, fw, piw, _, _ = oracle.solve(p2, pivot_rule=int(rule), config=_oracle_cfg(cfg), warm=st)
+        assert int(ns.Solve()) == rw.status == 1 and ns.GetMetrics().warm_started == 1, (case, int(rule))
+        assert ns.GetMetrics().iterations == rw.iterations and ns.GetTotalCost() == rw.total_cost, (case, int(rule), ns.GetMetrics().iterations, rw.iterations)
+        assert np.array_equal(ns.flows(), fw) and np.array_equal(ns.potentials(), piw), (case, int(rule))
+        warm_checked += 1
+    assert warm_checked >= 25, warm_checked
+
+
 def test_batch_of_64_instances_of_2_18_nodes():
     """BASELINE.json config 5 itself on one GPU: 64 independent NETGEN-8 2^18-node instances, four side by side; every instance
     bit-exact against what the CPU oracle recorded (tests/golden/batch18.json: pivots, cost, sha256 of flow[] and pi[])."""

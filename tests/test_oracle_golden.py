@@ -230,3 +230,39 @@ def test_oracle_warm_start_reaches_the_cold_optimum():
         assert oracle.validate(p2, fw, piw, rw.total_cost)[0] == 0, rule
         if oracle.lemon_available():
             assert oracle.lemon_solve(p2)["cost"] == rw.total_cost
+
+
+def test_oracle_warm_start_and_list_rules_on_random_small_networks():
+    """120 random small networks (some infeasible, some with lower bounds): every pivot rule of the restatement - the two list rules
+    included - agrees on status and optimal cost with the vendored LEMON build, and a warm start after random cost edits reaches
+    the cold optimum of the edited network."""
+    import copy
+    from conftest import random_small_problem
+    rng = np.random.default_rng(20261019)
+    checked = 0
+    for case in range(120):
+        p = random_small_problem(rng, case)
+        if p is None:
+            continue
+        n, m, cost = p.n, p.m, p.cost
+        ref = oracle.lemon_solve(p) if oracle.lemon_available() else None
+        st = oracle.State(n, m)
+        base, *_ = oracle.solve(p, auto_config=False, save=st)
+        for rule in (oracle.FIRST_ELIGIBLE, oracle.BEST_ELIGIBLE, oracle.BLOCK_SEARCH, oracle.CANDIDATE_LIST, oracle.ALTERING_LIST):
+            r, flow, pi, _, _ = oracle.solve(p, pivot_rule=rule, auto_config=False)
+            assert r.status == base.status, (case, rule, r.status, base.status)
+            if r.status == 1:
+                assert r.total_cost == base.total_cost and oracle.validate(p, flow, pi, r.total_cost)[0] == 0, (case, rule)
+        if ref is not None and base.status in (1, 2) and ref["status"] in (1, 2):
+            assert ref["status"] == base.status and (base.status != 1 or ref["cost"] == base.total_cost), (case, ref["status"], base.status)
+        if base.status != 1:
+            continue
+        p2 = copy.copy(p); p2.cost = cost.copy()
+        idx = rng.choice(m, max(1, m // 5), replace=False); p2.cost[idx] = rng.integers(1, 40, idx.size)
+        cold, *_ = oracle.solve(p2, auto_config=False)
+        for rule in (oracle.BLOCK_SEARCH, oracle.CANDIDATE_LIST, oracle.ALTERING_LIST):
+            warm, wf, wpi, _, _ = oracle.solve(p2, pivot_rule=rule, auto_config=False, warm=st)
+            assert warm.status == cold.status == 1 and warm.total_cost == cold.total_cost, (case, rule, warm.status, warm.total_cost, cold.total_cost)
+            assert oracle.validate(p2, wf, wpi, warm.total_cost)[0] == 0, (case, rule)
+        checked += 1
+    assert checked >= 40, checked
