@@ -34,7 +34,10 @@ enum : int {
 // Internal/BlockSearchPivotOptimized.cs:39-157; 5 / 6 = the Candidate List / Altering List rules PivotRule.cs:33-40 declares and
 // NS.cs:884 throws on, defined as LEMON's network_simplex.h:413-518 / :521-635)
 enum : int { PK_FIRST = 0, PK_BEST = 1, PK_BLOCK = 2, PK_BLOCK_CACHED = 3, PK_BLOCK_OPT = 4, PK_CAND_LIST = 5, PK_ALT_LIST = 6 };
-constexpr int kSortCap = 4096;          // Altering List: entries sorted per pass in shared memory (16 B each, in the cycle-list staging area)
+#ifndef MCF_SORT_CAP
+#define MCF_SORT_CAP 4096
+#endif
+constexpr int kSortCap = MCF_SORT_CAP;          // Altering List: entries sorted per pass in shared memory (16 B each, in the cycle-list staging area)
 
 struct __align__(16) PriceRec {         // one pricing candidate (per CTA, per round)
     long long c;                        // reduced cost (negative when valid, 0 = none)
